@@ -1,0 +1,119 @@
+/*
+ * vitb200.h — C ABI of libvitb200.so: the sm_100a (B200) kernels behind the vit.triton host API.
+ *
+ * Every entry point
+ *   - takes raw DEVICE pointers, integer sizes / element strides, a dtype enum and a cudaStream_t
+ *     (passed as void*); no torch / C++ types cross the boundary;
+ *   - enqueues work on the given stream and returns immediately (never synchronises, never
+ *     allocates device memory, safe inside CUDA-graph capture);
+ *   - returns 0 on success, a NEGATIVE vt_status for argument errors, or a POSITIVE cudaError_t.
+ *
+ * The reference (cmeraki/vit.triton) has no native boundary: its kernels are Triton functions
+ * called from Python.  Each declaration below cites the reference Python entry point it replaces;
+ * the Python shim in vit.triton_b200/vit/kernels/ keeps those names and signatures and calls this
+ * ABI through ctypes.
+ */
+#ifndef VITB200_H_
+#define VITB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  VT_OK = 0,
+  VT_ERR_ARG = -1,         /* bad shape / null pointer */
+  VT_ERR_DTYPE = -2,       /* unsupported dtype */
+  VT_ERR_ALIGN = -3,       /* pointer or stride alignment not met for the tensor-core path */
+  VT_ERR_UNSUPPORTED = -4, /* shape outside what this kernel implements */
+  VT_ERR_DRIVER = -5       /* cuTensorMapEncodeTiled unavailable / failed */
+} vt_status;
+
+typedef enum { VT_F32 = 0, VT_BF16 = 1 } vt_dtype;
+
+/* Library version (major*10000 + minor*100 + patch). */
+int vt_version(void);
+
+/* Human-readable text for a status returned by any function below (static storage). */
+const char* vt_status_string(int status);
+
+/* K4 — LayerNorm over the last dim of a [rows, dim] matrix; biased variance, eps inside sqrt.
+ * Replaces layernorm_triton / LayerNormTriton.forward (vit/kernels/layernorm.py:90-127,129-142).
+ * in/out dtype pairs: f32->f32, bf16->bf16, f32->bf16.  gamma/beta have the INPUT dtype. */
+int vt_layernorm(const void* x, const void* gamma, const void* beta, void* out, int64_t rows,
+                 int32_t dim, int64_t in_row_stride, int64_t out_row_stride, float eps,
+                 int32_t in_dtype, int32_t out_dtype, void* stream);
+
+/* K5 — out = a + b over n contiguous elements.  Replaces add_triton (vit/kernels/add.py:67-104). */
+int vt_add(const void* a, const void* b, void* out, int64_t n, int32_t dtype, void* stream);
+
+/* K6 — softmax over the last dim of [rows, cols] (input row stride in elements, output dense).
+ * Replaces softmax_triton (vit/kernels/softmax.py:36-74). */
+int vt_softmax(const void* x, void* out, int64_t rows, int32_t cols, int64_t in_row_stride,
+               int32_t dtype, void* stream);
+
+/* K1 — tensor-core GEMM (tcgen05 + TMEM + TMA):  out[M,N] = epi(A[M,K] . Bt[N,K]^T + bias).
+ * A, Bt bf16, K-major (row strides lda / ldb in elements, multiples of 8; K, N multiples of 8).
+ * out / residual: bf16 or f32 (out_dtype); bias: f32 or NULL; gelu: exact-erf GELU;
+ * residual (nullable) is added after the bias and may alias out.
+ * Replaces matmul_triton (vit/kernels/matmul.py:111-156) for the model's dense layers and folds
+ * add_triton (vit/vit.py:140,147) into the epilogue. */
+int vt_gemm_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, void* out, int64_t ldo,
+                 int32_t out_dtype, const float* bias, const void* residual, int64_t ldr,
+                 int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream);
+
+/* Generic strided batched GEMM on the FP32 pipe (exact-fp32 path and odd shapes):
+ *   C[z] = scale * act(A[z] . B[z] + bias),  z = zo * batch_inner + zi
+ * strides (elements): sA = {outer, inner, m, k}, sB = {outer, inner, k, n}, sC = {outer, inner, m, n}.
+ * All tensors share `dtype`; bias nullable.
+ * Replaces matmul_triton (matmul.py:111-156) and matmul3's matmul_triton (matmul3.py:111-156)
+ * wherever the tensor-core path's alignment rules do not hold. */
+int vt_gemm_strided(const void* A, const void* B, void* C, const void* bias, int32_t M, int32_t N,
+                    int32_t K, int32_t batch_outer, int32_t batch_inner, const int64_t* sA,
+                    const int64_t* sB, const int64_t* sC, float scale, int32_t gelu, int32_t dtype,
+                    void* stream);
+
+/* K3 — fused attention forward (tcgen05, flash style, no materialised scores), bf16, head dim 64.
+ * q/k/v: [B, N, H*dh] views with common row / batch strides (e.g. slices of a fused-QKV buffer);
+ * out: [B, N, H*dh].  Replaces the per-head matmul3 -> softmax -> matmul3 -> slice-assign chain
+ * (vit/vit.py:60-72,101-108). */
+int vt_flash_attn(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H,
+                  int32_t N, int32_t dh, int64_t qkv_row_stride, int64_t qkv_batch_stride,
+                  int64_t out_row_stride, int64_t out_batch_stride, float scale, void* stream);
+
+/* K2 — patch embedding (im2col-free tcgen05 GEMM) with CLS + position embedding fused:
+ * pixels [B,C,S,S] (pix_dtype f32|bf16); w [D, C*P*P] bf16 (row stride ldw); posb [n+1, D] f32 =
+ * pos + (row 0: cls, rows >= 1: conv bias); out [B, n+1, D] (out_dtype).
+ * Replaces Conv2DTriton.forward + Embeddings.forward glue (conv2d.py:100-167, vit/vit.py:188-200). */
+int vt_patch_embed(const void* pixels, int32_t pix_dtype, const void* w, int64_t ldw,
+                   const float* posb, void* out, int32_t out_dtype, int32_t B, int32_t C, int32_t S,
+                   int32_t P, int32_t D, void* stream);
+
+/* (B,C,H,W) -> (B, (H/P)*(W/P), C*P*P) patch rows in (c,i,j) order.
+ * Replaces patching_triton (vit/kernels/patching.py:54-92). */
+int vt_patching(const void* image, void* out, int32_t B, int32_t C, int32_t H, int32_t W, int32_t P,
+                int32_t dtype, void* stream);
+
+/* x[b,0,:] = cls + pos[0];  x[b,t,:] += pos[t] for t >= 1, in place on x [B,N,D].
+ * Replaces torch.cat(cls) and the broadcast + position_embeddings (vit/vit.py:195-200). */
+int vt_embed_finalize(void* x, const void* pos, const void* cls, int32_t B, int32_t N, int32_t D,
+                      int32_t dtype, void* stream);
+
+/* Stride == kernel convolution, NCHW in / NCHW out, any kernel shape.
+ * Replaces conv2d_triton (vit/kernels/conv2d.py:100-150) as a standalone entry point. */
+int vt_conv2d(const void* input, const void* weight, const void* bias, void* out, int32_t B,
+              int32_t C, int32_t H, int32_t W, int32_t O, int32_t kh, int32_t kw, int32_t dtype,
+              void* stream);
+
+/* K7 — out[b,:] = x[b,0,:]: CLS rows of the final hidden states, the tensor the data-parallel
+ * wrapper all-gathers.  (New: the reference has no pooling / multi-GPU step.) */
+int vt_pool_cls(const void* x, void* out, int32_t B, int32_t D, int64_t batch_stride, int32_t dtype,
+                void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* VITB200_H_ */

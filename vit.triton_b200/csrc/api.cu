@@ -1,0 +1,117 @@
+// extern "C" surface of libvitb200.so (declared in include/vitb200.h).  Thin: argument plumbing
+// only, all kernels live in the other translation units.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vitb200.h"
+
+namespace vt {
+int layernorm_rows(const void*, const void*, const void*, void*, long long, int, long long,
+                   long long, float, int, int, cudaStream_t);
+int add_elementwise(const void*, const void*, void*, long long, int, cudaStream_t);
+int softmax_rows(const void*, void*, long long, int, long long, int, cudaStream_t);
+int pool_cls(const void*, void*, int, int, long long, int, cudaStream_t);
+int gemm_bf16_tcgen05(const void*, long long, const void*, long long, void*, long long, int,
+                      const float*, const void*, long long, int, int, int, int, cudaStream_t);
+int simt_gemm(const void*, const void*, void*, const void*, int, int, int, int, int,
+              const long long*, const long long*, const long long*, float, int, int, cudaStream_t);
+int attn_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
+                     long long, long long, long long, float, cudaStream_t);
+int patch_embed_tcgen05(const void*, int, const void*, long long, const float*, void*, int, int,
+                        int, int, int, int, cudaStream_t);
+int patching(const void*, void*, int, int, int, int, int, int, cudaStream_t);
+int embed_finalize(void*, const void*, const void*, int, int, int, int, cudaStream_t);
+int conv2d_nchw(const void*, const void*, const void*, void*, int, int, int, int, int, int, int,
+                int, cudaStream_t);
+}  // namespace vt
+
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int vt_version(void) { return 100; }
+
+const char* vt_status_string(int status) {
+  switch (status) {
+    case VT_OK: return "ok";
+    case VT_ERR_ARG: return "invalid argument (null pointer or bad shape)";
+    case VT_ERR_DTYPE: return "unsupported dtype";
+    case VT_ERR_ALIGN: return "pointer/stride alignment not met for the tensor-core path";
+    case VT_ERR_UNSUPPORTED: return "shape not supported by this kernel";
+    case VT_ERR_DRIVER: return "cuTensorMapEncodeTiled unavailable or failed";
+    default:
+      if (status > 0) return cudaGetErrorString(static_cast<cudaError_t>(status));
+      return "unknown status";
+  }
+}
+
+int vt_layernorm(const void* x, const void* gamma, const void* beta, void* out, int64_t rows,
+                 int32_t dim, int64_t in_row_stride, int64_t out_row_stride, float eps,
+                 int32_t in_dtype, int32_t out_dtype, void* stream) {
+  return vt::layernorm_rows(x, gamma, beta, out, rows, dim, in_row_stride, out_row_stride, eps,
+                            in_dtype, out_dtype, S(stream));
+}
+
+int vt_add(const void* a, const void* b, void* out, int64_t n, int32_t dtype, void* stream) {
+  return vt::add_elementwise(a, b, out, n, dtype, S(stream));
+}
+
+int vt_softmax(const void* x, void* out, int64_t rows, int32_t cols, int64_t in_row_stride,
+               int32_t dtype, void* stream) {
+  return vt::softmax_rows(x, out, rows, cols, in_row_stride, dtype, S(stream));
+}
+
+int vt_gemm_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, void* out, int64_t ldo,
+                 int32_t out_dtype, const float* bias, const void* residual, int64_t ldr,
+                 int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream) {
+  return vt::gemm_bf16_tcgen05(A, lda, Bt, ldb, out, ldo, out_dtype, bias, residual, ldr, M, N, K,
+                               gelu, S(stream));
+}
+
+int vt_gemm_strided(const void* A, const void* B, void* C, const void* bias, int32_t M, int32_t N,
+                    int32_t K, int32_t batch_outer, int32_t batch_inner, const int64_t* sA,
+                    const int64_t* sB, const int64_t* sC, float scale, int32_t gelu, int32_t dtype,
+                    void* stream) {
+  if (!sA || !sB || !sC) return VT_ERR_ARG;
+  long long a[4], b[4], c[4];
+  for (int i = 0; i < 4; ++i) { a[i] = sA[i]; b[i] = sB[i]; c[i] = sC[i]; }
+  return vt::simt_gemm(A, B, C, bias, M, N, K, batch_outer, batch_inner, a, b, c, scale, gelu,
+                       dtype, S(stream));
+}
+
+int vt_flash_attn(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H,
+                  int32_t N, int32_t dh, int64_t qkv_row_stride, int64_t qkv_batch_stride,
+                  int64_t out_row_stride, int64_t out_batch_stride, float scale, void* stream) {
+  return vt::attn_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
+                              out_row_stride, out_batch_stride, scale, S(stream));
+}
+
+int vt_patch_embed(const void* pixels, int32_t pix_dtype, const void* w, int64_t ldw,
+                   const float* posb, void* out, int32_t out_dtype, int32_t B, int32_t C, int32_t S_,
+                   int32_t P, int32_t D, void* stream) {
+  return vt::patch_embed_tcgen05(pixels, pix_dtype, w, ldw, posb, out, out_dtype, B, C, S_, P, D,
+                                 S(stream));
+}
+
+int vt_patching(const void* image, void* out, int32_t B, int32_t C, int32_t H, int32_t W, int32_t P,
+                int32_t dtype, void* stream) {
+  return vt::patching(image, out, B, C, H, W, P, dtype, S(stream));
+}
+
+int vt_embed_finalize(void* x, const void* pos, const void* cls, int32_t B, int32_t N, int32_t D,
+                      int32_t dtype, void* stream) {
+  return vt::embed_finalize(x, pos, cls, B, N, D, dtype, S(stream));
+}
+
+int vt_conv2d(const void* input, const void* weight, const void* bias, void* out, int32_t B,
+              int32_t C, int32_t H, int32_t W, int32_t O, int32_t kh, int32_t kw, int32_t dtype,
+              void* stream) {
+  return vt::conv2d_nchw(input, weight, bias, out, B, C, H, W, O, kh, kw, dtype, S(stream));
+}
+
+int vt_pool_cls(const void* x, void* out, int32_t B, int32_t D, int64_t batch_stride, int32_t dtype,
+                void* stream) {
+  return vt::pool_cls(x, out, B, D, batch_stride, dtype, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,337 @@
+// K2: patch embedding as an im2col-free tcgen05 GEMM with the CLS / position-embedding add fused
+// into the epilogue.
+//
+//   out[b, 0, :]     = cls + pos[0]
+//   out[b, 1 + p, :] = sum_k patch(b,p)[k] * W[:, k] + bias + pos[1 + p]      k = (c, i, j)
+//
+// Replaces conv2d_kernel (reference vit/kernels/conv2d.py:19-97: one program per (image, output
+// channel, output row), scalar tl.sum, every patch re-read D times) plus the torch glue after it
+// (flatten/transpose, cat(cls), + position_embeddings: vit/vit.py:190-200).
+//
+// A (the patches) is never materialised: four producer warps gather 128 patches x 64 k straight
+// from the NCHW pixels into the SWIZZLE_128B K-major smem layout the UMMA descriptor expects
+// (TMA cannot express a 14-pixel, 28-byte inner box, and C=3 rules out im2col-mode TMA).
+// B (conv weight viewed as [D, 3*P*P], already K-major) arrives by TMA.
+//   warp 0      TMA producer for B + TMEM alloc
+//   warp 1      MMA issuer (M=128, N=256, K=16)
+//   warps 2-5   A gather producers, then epilogue (TMEM -> + posb -> global)
+#include "common.cuh"
+#include "tensormap.h"
+
+namespace vt {
+
+namespace {
+
+constexpr int PE_BM = 128;
+constexpr int PE_BN = 256;
+constexpr int PE_BK = 64;
+constexpr int PE_STAGES = 4;
+constexpr int PE_THREADS = 192;
+constexpr int PE_A_BYTES = PE_BM * PE_BK * 2;
+constexpr int PE_B_BYTES = PE_BN * PE_BK * 2;
+constexpr int PE_STAGE_BYTES = PE_A_BYTES + PE_B_BYTES;
+constexpr int PE_SMEM = 1024 + PE_STAGES * PE_STAGE_BYTES + 256;
+
+struct PatchParams {
+  const void* pixels;   // [B, C, S, S]
+  int B, C, S, P;
+  int grid_w;           // S / P
+  int n_patches;        // grid_w^2
+  int K;                // C * P * P
+  int D;
+  const float* posb;    // [n_patches + 1, D] fp32: pos + (cls | conv bias)
+  void* out;            // [B, n_patches + 1, D]
+  int out_f32;
+};
+
+__device__ __forceinline__ float px_to_f(float v) { return v; }
+__device__ __forceinline__ float px_to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename TPix>
+__global__ void __launch_bounds__(PE_THREADS, 1)
+patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const PatchParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const uint32_t bar_addr = smem_base + PE_STAGES * PE_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_addr + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_addr + 8u * (PE_STAGES + s); };
+  const uint32_t acc_bar = bar_addr + 8u * (2 * PE_STAGES);
+  const uint32_t tmem_slot = bar_addr + 8u * (2 * PE_STAGES + 1);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + PE_STAGES * PE_STAGE_BYTES + 8 * (2 * PE_STAGES + 1));
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_blk = blockIdx.x;
+  const int m_blk = blockIdx.y;
+  const int num_kb = (p.K + PE_BK - 1) / PE_BK;
+
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < PE_STAGES; ++s) {
+      mbar_init(full_bar(s), 1 + 128);  // TMA expect_tx arrive + 128 gather threads
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp_idx == 0) {
+    if (lane == 0) tma_prefetch_desc(&tma_w);
+    __syncwarp();
+    tmem_alloc<PE_BN>(tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp_idx == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(s), phase ^ 1u);
+        const uint32_t b_dst = smem_base + s * PE_STAGE_BYTES + PE_A_BYTES;
+        mbar_arrive_expect_tx(full_bar(s), PE_B_BYTES);
+        tma_load_2d(&tma_w, full_bar(s), b_dst, kb * PE_BK, n_blk * PE_BN, kEvictLast);
+        if (++s == PE_STAGES) { s = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp_idx == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(PE_BM, PE_BN, 0, 0);
+      int s = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(s), phase);
+        tc_fence_after();
+        const uint32_t a_src = smem_base + s * PE_STAGE_BYTES;
+        const uint32_t b_src = a_src + PE_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < PE_BK / 16; ++k) {
+          umma_ss(tmem_base, make_desc_kmajor_sw128(a_src + k * 32),
+                  make_desc_kmajor_sw128(b_src + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));
+        if (++s == PE_STAGES) { s = 0; phase ^= 1u; }
+      }
+      umma_commit(acc_bar);
+    }
+  } else {
+    // ------------------------------------------------------------ gather producers (128 threads)
+    const int r = threadIdx.x - 64;  // tile row owned by this thread, 0..127
+    const long long m = static_cast<long long>(m_blk) * PE_BM + r;
+    const bool row_valid = m < static_cast<long long>(p.B) * p.n_patches;
+    const int img = row_valid ? static_cast<int>(m / p.n_patches) : 0;
+    const int patch = row_valid ? static_cast<int>(m - static_cast<long long>(img) * p.n_patches) : 0;
+    const int py = patch / p.grid_w;
+    const int px = patch - py * p.grid_w;
+    const TPix* img_base = static_cast<const TPix*>(p.pixels) +
+                           static_cast<long long>(img) * p.C * p.S * p.S +
+                           static_cast<long long>(py) * p.P * p.S + px * p.P;
+    const int PP = p.P * p.P;
+    const bool vec_ok = (p.P % 8 == 0) && (p.S % 8 == 0);
+
+    int s = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(empty_bar(s), phase ^ 1u);
+      uint8_t* a_row = smem_gen + s * PE_STAGE_BYTES + r * 128;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const int k0 = kb * PE_BK + ch * 8;
+        uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+        if (row_valid && k0 < p.K) {
+          if (vec_ok) {
+            const int c = k0 / PP;
+            const int rem = k0 - c * PP;
+            const int i = rem / p.P;
+            const int j = rem - i * p.P;
+            const TPix* src = img_base + (static_cast<long long>(c) * p.S + i) * p.S + j;
+            if constexpr (sizeof(TPix) == 2) {
+              packed = __ldg(reinterpret_cast<const uint4*>(src));
+            } else {
+              const float4 f0 = __ldg(reinterpret_cast<const float4*>(src));
+              const float4 f1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+              packed.x = pack_bf16x2(f0.x, f0.y);
+              packed.y = pack_bf16x2(f0.z, f0.w);
+              packed.z = pack_bf16x2(f1.x, f1.y);
+              packed.w = pack_bf16x2(f1.z, f1.w);
+            }
+          } else {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int k = k0 + e;
+              f[e] = 0.f;
+              if (k < p.K) {
+                const int c = k / PP;
+                const int rem = k - c * PP;
+                const int i = rem / p.P;
+                const int j = rem - i * p.P;
+                f[e] = px_to_f(img_base[(static_cast<long long>(c) * p.S + i) * p.S + j]);
+              }
+            }
+            packed.x = pack_bf16x2(f[0], f[1]);
+            packed.y = pack_bf16x2(f[2], f[3]);
+            packed.z = pack_bf16x2(f[4], f[5]);
+            packed.w = pack_bf16x2(f[6], f[7]);
+          }
+        }
+        *reinterpret_cast<uint4*>(a_row + ((ch ^ (r & 7)) << 4)) = packed;
+      }
+      fence_proxy_async_smem();  // make generic-proxy smem writes visible to the tensor core
+      mbar_arrive(full_bar(s));
+      if (++s == PE_STAGES) { s = 0; phase ^= 1u; }
+    }
+
+    // ------------------------------------------------------------ epilogue
+    const int quarter = warp_idx & 3;
+    // TMEM lane == tile row; this warp may only read lanes [32*quarter, 32*quarter+32)
+    const int er = quarter * 32 + lane;
+    const long long em = static_cast<long long>(m_blk) * PE_BM + er;
+    const bool e_valid = em < static_cast<long long>(p.B) * p.n_patches;
+    const int e_img = e_valid ? static_cast<int>(em / p.n_patches) : 0;
+    const int e_patch = e_valid ? static_cast<int>(em - static_cast<long long>(e_img) * p.n_patches) : 0;
+    const int n_tok = p.n_patches + 1;
+    const long long out_row = static_cast<long long>(e_img) * n_tok + 1 + e_patch;
+    const float* posb_row = p.posb + static_cast<long long>(1 + e_patch) * p.D;
+
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < PE_BN; c += 32) {
+      const int col = n_blk * PE_BN + c;
+      uint32_t rr[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c, rr);
+      tmem_ld_wait();
+      if (!e_valid || col >= p.D) continue;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col + i + 3 < p.D) {
+          pb = __ldg(reinterpret_cast<const float4*>(posb_row + col + i));
+        } else {
+          if (col + i + 0 < p.D) pb.x = posb_row[col + i + 0];
+          if (col + i + 1 < p.D) pb.y = posb_row[col + i + 1];
+          if (col + i + 2 < p.D) pb.z = posb_row[col + i + 2];
+        }
+        v[i + 0] = __uint_as_float(rr[i + 0]) + pb.x;
+        v[i + 1] = __uint_as_float(rr[i + 1]) + pb.y;
+        v[i + 2] = __uint_as_float(rr[i + 2]) + pb.z;
+        v[i + 3] = __uint_as_float(rr[i + 3]) + pb.w;
+      }
+      const bool full_chunk = col + 32 <= p.D;
+      if (p.out_f32) {
+        float* o = static_cast<float*>(p.out) + out_row * p.D + col;
+        if (full_chunk) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+          for (int i = 0; i < 32 && col + i < p.D; ++i) o[i] = v[i];
+        }
+      } else {
+        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + out_row * p.D + col;
+        if (full_chunk) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 o4;
+            o4.x = pack_bf16x2(v[i + 0], v[i + 1]);
+            o4.y = pack_bf16x2(v[i + 2], v[i + 3]);
+            o4.z = pack_bf16x2(v[i + 4], v[i + 5]);
+            o4.w = pack_bf16x2(v[i + 6], v[i + 7]);
+            *reinterpret_cast<uint4*>(o + i) = o4;
+          }
+        } else {
+          for (int i = 0; i < 32 && col + i < p.D; ++i) o[i] = __float2bfloat16_rn(v[i]);
+        }
+      }
+    }
+
+    // CLS rows: the first row-tile of every column block writes cls + pos[0] for all images.
+    if (m_blk == 0) {
+      const int ncols = min(PE_BN, p.D - n_blk * PE_BN);
+      const int total = p.B * ncols;
+      for (int idx = r; idx < total; idx += 128) {
+        const int b = idx / ncols;
+        const int c = idx - b * ncols;
+        const int col = n_blk * PE_BN + c;
+        const float val = p.posb[col];
+        const long long off = static_cast<long long>(b) * n_tok * p.D + col;
+        if (p.out_f32) static_cast<float*>(p.out)[off] = val;
+        else static_cast<__nv_bfloat16*>(p.out)[off] = __float2bfloat16_rn(val);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<PE_BN>(tmem_base);
+  }
+}
+
+}  // namespace
+
+// pixels [B,C,S,S] (fp32 or bf16), w [D, C*P*P] bf16 with row stride ldw (elements, multiple of 8),
+// posb [n+1, D] fp32, out [B, n+1, D] bf16|f32.
+int patch_embed_tcgen05(const void* pixels, int pix_dtype, const void* w, long long ldw,
+                        const float* posb, void* out, int out_dtype, int B, int C, int S, int P,
+                        int D, cudaStream_t stream) {
+  if (!pixels || !w || !posb || !out || B <= 0 || C <= 0 || S <= 0 || P <= 0 || D <= 0)
+    return VT_ERR_ARG;
+  if (S % P) return VT_ERR_ARG;
+  if ((ldw % 8) || (D % 8)) return VT_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(pixels) | reinterpret_cast<uintptr_t>(w) |
+       reinterpret_cast<uintptr_t>(posb) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return VT_ERR_ALIGN;
+  const int K = C * P * P;
+  CUtensorMap tw;
+  int rc = make_tmap_bf16_2d(&tw, w, K, D, ldw, PE_BK, PE_BN, TMAP_SW_128);
+  if (rc) return rc;
+
+  PatchParams p;
+  p.pixels = pixels;
+  p.B = B; p.C = C; p.S = S; p.P = P;
+  p.grid_w = S / P;
+  p.n_patches = p.grid_w * p.grid_w;
+  p.K = K;
+  p.D = D;
+  p.posb = posb;
+  p.out = out;
+  p.out_f32 = (out_dtype == VT_F32);
+  if (out_dtype != VT_F32 && out_dtype != VT_BF16) return VT_ERR_DTYPE;
+
+  const long long M = static_cast<long long>(B) * p.n_patches;
+  dim3 grid((D + PE_BN - 1) / PE_BN, static_cast<unsigned>((M + PE_BM - 1) / PE_BM));
+  if (grid.y > 65535) return VT_ERR_UNSUPPORTED;
+  static bool attr_f32 = false, attr_bf16 = false;
+  if (pix_dtype == VT_F32) {
+    auto kern = patch_embed_tcgen05_kernel<float>;
+    if (!attr_f32) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PE_SMEM);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      attr_f32 = true;
+    }
+    kern<<<grid, PE_THREADS, PE_SMEM, stream>>>(tw, p);
+  } else if (pix_dtype == VT_BF16) {
+    auto kern = patch_embed_tcgen05_kernel<__nv_bfloat16>;
+    if (!attr_bf16) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PE_SMEM);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      attr_bf16 = true;
+    }
+    kern<<<grid, PE_THREADS, PE_SMEM, stream>>>(tw, p);
+  } else {
+    return VT_ERR_DTYPE;
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace vt

@@ -1,0 +1,352 @@
+// Bandwidth-bound kernels: LayerNorm (K4), elementwise add (K5), row softmax (K6), CLS pooling (K7).
+// All are vectorised (16-byte accesses), coalesced and warp-reduced; none uses shared memory
+// because no element is touched by more than one thread.
+//
+// Reference semantics reproduced:
+//   layernorm  vit/kernels/layernorm.py:51-85  (mean; biased variance of centred values;
+//              w*(x-mean)/sqrt(var+eps)+b)
+//   add        vit/kernels/add.py:60-65
+//   softmax    vit/kernels/softmax.py:26-31    (max-subtracted exp / sum over the last dim)
+#include "common.cuh"
+
+namespace vt {
+
+namespace {
+
+template <typename T>
+struct Vec;  // 16-byte vector of T
+
+template <>
+struct Vec<float> {
+  static constexpr int N = 4;
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+template <>
+struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  float v[8];
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    v[0] = bf16_lo(t.x); v[1] = bf16_hi(t.x);
+    v[2] = bf16_lo(t.y); v[3] = bf16_hi(t.y);
+    v[4] = bf16_lo(t.z); v[5] = bf16_hi(t.z);
+    v[6] = bf16_lo(t.w); v[7] = bf16_hi(t.w);
+  }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const {
+    uint4 t;
+    t.x = pack_bf16x2(v[0], v[1]);
+    t.y = pack_bf16x2(v[2], v[3]);
+    t.z = pack_bf16x2(v[4], v[5]);
+    t.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ void from_f(float* p, float x) { *p = x; }
+__device__ __forceinline__ void from_f(__nv_bfloat16* p, float x) { *p = __float2bfloat16_rn(x); }
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, the row lives in registers (VPL 16-byte vectors per lane), so HBM
+// sees exactly one read and one write of the activation.
+// ------------------------------------------------------------------------------------------
+template <typename T, typename TO, int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
+                      const T* __restrict__ beta, TO* __restrict__ out, long long rows, int dim,
+                      long long in_stride, long long out_stride, float eps) {
+  constexpr int EV = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* xr = x + row * in_stride;
+  const int nvec = dim / EV;
+
+  Vec<T> d[VPL];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      d[i].load(xr + vi * EV);
+#pragma unroll
+      for (int e = 0; e < EV; ++e) sum += d[i].v[e];
+    }
+  }
+  const float mean = warp_sum(sum) / static_cast<float>(dim);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int e = 0; e < EV; ++e) {
+        const float c = d[i].v[e] - mean;
+        sq += c * c;
+      }
+    }
+  }
+  const float var = warp_sum(sq) / static_cast<float>(dim);
+  const float rstd = 1.0f / sqrtf(var + eps);
+
+  TO* orow = out + row * out_stride;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      Vec<T> g, b;
+      g.load(gamma + vi * EV);
+      b.load(beta + vi * EV);
+      if constexpr (sizeof(TO) == sizeof(T)) {
+        Vec<TO> o;
+#pragma unroll
+        for (int e = 0; e < EV; ++e) o.v[e] = g.v[e] * ((d[i].v[e] - mean) * rstd) + b.v[e];
+        o.store(orow + vi * EV);
+      } else {
+        // fp32 in, bf16 out: 4 values -> 8 bytes
+        static_assert(EV == 4, "mixed LN is fp32 -> bf16 only");
+        uint2 o;
+        o.x = pack_bf16x2(g.v[0] * ((d[i].v[0] - mean) * rstd) + b.v[0],
+                          g.v[1] * ((d[i].v[1] - mean) * rstd) + b.v[1]);
+        o.y = pack_bf16x2(g.v[2] * ((d[i].v[2] - mean) * rstd) + b.v[2],
+                          g.v[3] * ((d[i].v[3] - mean) * rstd) + b.v[3]);
+        *reinterpret_cast<uint2*>(orow + vi * EV) = o;
+      }
+    }
+  }
+}
+
+// Generic fallback (any dim / alignment): one warp per row, three passes over L1/L2-resident data.
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256)
+layernorm_generic_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
+                         const T* __restrict__ beta, TO* __restrict__ out, long long rows, int dim,
+                         long long in_stride, long long out_stride, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* xr = x + row * in_stride;
+  float sum = 0.f;
+  for (int i = lane; i < dim; i += 32) sum += to_f(xr[i]);
+  const float mean = warp_sum(sum) / static_cast<float>(dim);
+  float sq = 0.f;
+  for (int i = lane; i < dim; i += 32) {
+    const float c = to_f(xr[i]) - mean;
+    sq += c * c;
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / static_cast<float>(dim) + eps);
+  TO* orow = out + row * out_stride;
+  for (int i = lane; i < dim; i += 32)
+    from_f(orow + i, to_f(gamma[i]) * ((to_f(xr[i]) - mean) * rstd) + to_f(beta[i]));
+}
+
+template <typename T, typename TO>
+int launch_layernorm(const void* x, const void* g, const void* b, void* out, long long rows,
+                     int dim, long long in_stride, long long out_stride, float eps,
+                     cudaStream_t stream) {
+  constexpr int EV = Vec<T>::N;
+  const int warps = 8;
+  const unsigned grid = static_cast<unsigned>((rows + warps - 1) / warps);
+  const T* xp = static_cast<const T*>(x);
+  const T* gp = static_cast<const T*>(g);
+  const T* bp = static_cast<const T*>(b);
+  TO* op = static_cast<TO*>(out);
+  const bool aligned =
+      (dim % EV == 0) && (in_stride % EV == 0) && (out_stride % EV == 0) &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g) |
+        reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+  const int vpl = aligned ? (dim / EV + 31) / 32 : 0;
+#define VT_LN_CASE(V)                                                                        \
+  case V:                                                                                    \
+    layernorm_rows_kernel<T, TO, V><<<grid, warps * 32, 0, stream>>>(xp, gp, bp, op, rows, dim, \
+                                                                     in_stride, out_stride, eps); \
+    break;
+  switch (vpl) {
+    VT_LN_CASE(1) VT_LN_CASE(2) VT_LN_CASE(3) VT_LN_CASE(4) VT_LN_CASE(5) VT_LN_CASE(6)
+    VT_LN_CASE(7) VT_LN_CASE(8) VT_LN_CASE(10) VT_LN_CASE(12) VT_LN_CASE(16)
+    default:
+      layernorm_generic_kernel<T, TO><<<grid, warps * 32, 0, stream>>>(xp, gp, bp, op, rows, dim,
+                                                                       in_stride, out_stride, eps);
+  }
+#undef VT_LN_CASE
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------
+// add: out = a + b, 16-byte vectors, 4 independent loads in flight per thread
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+add_vec_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
+               long long nvec) {
+  constexpr int EV = Vec<T>::N;
+  constexpr int U = 4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + (U - 1) * stride < nvec; i += U * stride) {
+    Vec<T> va[U], vb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      va[u].load(a + (i + u * stride) * EV);
+      vb[u].load(b + (i + u * stride) * EV);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int e = 0; e < EV; ++e) va[u].v[e] += vb[u].v[e];
+      va[u].store(out + (i + u * stride) * EV);
+    }
+  }
+  for (; i < nvec; i += stride) {
+    Vec<T> va, vb;
+    va.load(a + i * EV);
+    vb.load(b + i * EV);
+#pragma unroll
+    for (int e = 0; e < EV; ++e) va.v[e] += vb.v[e];
+    va.store(out + i * EV);
+  }
+}
+
+template <typename T>
+__global__ void add_scalar_kernel(const T* __restrict__ a, const T* __restrict__ b,
+                                  T* __restrict__ out, long long start, long long n) {
+  const long long i = start + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) from_f(out + i, to_f(a[i]) + to_f(b[i]));
+}
+
+template <typename T>
+int launch_add(const void* a, const void* b, void* out, long long n, cudaStream_t stream) {
+  constexpr int EV = Vec<T>::N;
+  const T* ap = static_cast<const T*>(a);
+  const T* bp = static_cast<const T*>(b);
+  T* op = static_cast<T*>(out);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+                         reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+  long long done = 0;
+  if (aligned && n >= EV) {
+    const long long nvec = n / EV;
+    long long blocks = (nvec + 256 * 4 - 1) / (256 * 4);
+    const long long cap = 148LL * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    add_vec_kernel<T><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(ap, bp, op, nvec);
+    done = nvec * EV;
+  }
+  if (done < n) {
+    const long long rem = n - done;
+    add_scalar_kernel<T><<<static_cast<unsigned>((rem + 255) / 256), 256, 0, stream>>>(ap, bp, op,
+                                                                                      done, n);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------
+// softmax over the last dim: one warp per row
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const T* __restrict__ x, T* __restrict__ out, long long rows, int cols,
+                    long long row_stride) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* xr = x + row * row_stride;
+  T* orow = out + row * static_cast<long long>(cols);
+  float m = -INFINITY;
+  for (int i = lane; i < cols; i += 32) m = fmaxf(m, to_f(xr[i]));
+  m = warp_max(m);
+  float s = 0.f;
+  for (int i = lane; i < cols; i += 32) s += expf(to_f(xr[i]) - m);
+  s = warp_sum(s);
+  const float inv = 1.0f / s;
+  for (int i = lane; i < cols; i += 32) from_f(orow + i, expf(to_f(xr[i]) - m) * inv);
+}
+
+// ------------------------------------------------------------------------------------------
+// pool: out[b, :] = x[b, 0, :]  (CLS row of the final hidden states)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pool_cls_kernel(const T* __restrict__ x, T* __restrict__ out, int batch, int dim,
+                                long long batch_stride) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(batch) * dim) return;
+  const int b = static_cast<int>(i / dim);
+  const int c = static_cast<int>(i - static_cast<long long>(b) * dim);
+  out[i] = x[b * batch_stride + c];
+}
+
+}  // namespace
+
+int layernorm_rows(const void* x, const void* gamma, const void* beta, void* out, long long rows,
+                   int dim, long long in_stride, long long out_stride, float eps, int in_dtype,
+                   int out_dtype, cudaStream_t stream) {
+  if (!x || !gamma || !beta || !out || rows < 0 || dim <= 0) return VT_ERR_ARG;
+  if (rows == 0) return VT_OK;
+  if (in_dtype == VT_F32 && out_dtype == VT_F32)
+    return launch_layernorm<float, float>(x, gamma, beta, out, rows, dim, in_stride, out_stride,
+                                          eps, stream);
+  if (in_dtype == VT_BF16 && out_dtype == VT_BF16)
+    return launch_layernorm<__nv_bfloat16, __nv_bfloat16>(x, gamma, beta, out, rows, dim,
+                                                          in_stride, out_stride, eps, stream);
+  if (in_dtype == VT_F32 && out_dtype == VT_BF16)
+    return launch_layernorm<float, __nv_bfloat16>(x, gamma, beta, out, rows, dim, in_stride,
+                                                  out_stride, eps, stream);
+  return VT_ERR_DTYPE;
+}
+
+int add_elementwise(const void* a, const void* b, void* out, long long n, int dtype,
+                    cudaStream_t stream) {
+  if (!a || !b || !out || n < 0) return VT_ERR_ARG;
+  if (n == 0) return VT_OK;
+  if (dtype == VT_F32) return launch_add<float>(a, b, out, n, stream);
+  if (dtype == VT_BF16) return launch_add<__nv_bfloat16>(a, b, out, n, stream);
+  return VT_ERR_DTYPE;
+}
+
+int softmax_rows(const void* x, void* out, long long rows, int cols, long long row_stride,
+                 int dtype, cudaStream_t stream) {
+  if (!x || !out || rows < 0 || cols <= 0) return VT_ERR_ARG;
+  if (rows == 0) return VT_OK;
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  if (dtype == VT_F32)
+    softmax_rows_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x),
+                                                         static_cast<float*>(out), rows, cols,
+                                                         row_stride);
+  else if (dtype == VT_BF16)
+    softmax_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), rows, cols,
+        row_stride);
+  else
+    return VT_ERR_DTYPE;
+  return static_cast<int>(cudaGetLastError());
+}
+
+int pool_cls(const void* x, void* out, int batch, int dim, long long batch_stride, int dtype,
+             cudaStream_t stream) {
+  if (!x || !out || batch < 0 || dim <= 0) return VT_ERR_ARG;
+  if (batch == 0) return VT_OK;
+  const long long n = static_cast<long long>(batch) * dim;
+  const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+  if (dtype == VT_F32)
+    pool_cls_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x),
+                                                     static_cast<float*>(out), batch, dim,
+                                                     batch_stride);
+  else if (dtype == VT_BF16)
+    pool_cls_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), batch, dim,
+        batch_stride);
+  else
+    return VT_ERR_DTYPE;
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace vt

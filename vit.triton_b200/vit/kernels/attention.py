@@ -1,0 +1,57 @@
+"""Fused multi-head attention — host entry point for K3.
+
+New relative to the reference, which runs heads serially through matmul3 / softmax / matmul3
+(vit/vit.py:56-74,97-108); the entry point takes the fused-QKV activation the packed QKV GEMM
+produces and returns the concatenated context in (B, N, D) layout.
+"""
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+def flash_attention(qkv: torch.Tensor, num_heads: int, scale: Optional[float] = None) -> torch.Tensor:
+    """qkv: (B, N, 3*D) with columns [Q | K | V], head h at columns h*dh:(h+1)*dh of each third.
+    Returns softmax(scale * Q K^T) V per head, concatenated: (B, N, D)."""
+    assert qkv.is_cuda, "Input is not on GPU"
+    assert len(qkv.shape) == 3 and qkv.shape[2] % (3 * num_heads) == 0, \
+        f"qkv needs to be (B, N, 3*D) with D divisible by num_heads, provided: {qkv.shape}, {num_heads}"
+    assert qkv.stride(2) == 1, "qkv last dimension needs to be contiguous"
+    B, N, D3 = qkv.shape
+    D = D3 // 3
+    dh = D // num_heads
+    if scale is None:
+        scale = 1.0 / math.sqrt(dh)
+    out = torch.empty((B, N, D), device=qkv.device, dtype=qkv.dtype)
+    if out.numel() == 0:
+        return out
+    es = qkv.element_size()
+    base = qkv.data_ptr()
+    stream = _lib.stream_ptr(qkv)
+
+    if qkv.dtype == torch.bfloat16 and dh == 64 and qkv.stride(1) % 8 == 0 and qkv.stride(0) % 8 == 0 \
+            and base % 16 == 0:
+        for b0 in range(0, B, 32768):
+            nb = min(32768, B - b0)
+            off = b0 * qkv.stride(0) * es
+            _lib.call("vt_flash_attn", base + off, base + off + D * es, base + off + 2 * D * es,
+                      out[b0:].data_ptr(), nb, num_heads, N, dh, qkv.stride(1), qkv.stride(0), D, N * D,
+                      float(scale), stream)
+        return out
+
+    # exact / odd-head-dim path: scores, softmax and PV as three strided launches over (B, H)
+    scores = torch.empty((B * num_heads, N, N), device=qkv.device, dtype=qkv.dtype)
+    probs = torch.empty_like(scores)
+    code = _lib.dtype_code(qkv)
+    sq = _lib.i64x4(qkv.stride(0), dh, qkv.stride(1), 1)
+    _lib.call("vt_gemm_strided", base, base + D * es, scores.data_ptr(), None, N, N, dh, B, num_heads,
+              sq, _lib.i64x4(qkv.stride(0), dh, 1, qkv.stride(1)),
+              _lib.i64x4(num_heads * N * N, N * N, N, 1), float(scale), 0, code, stream)
+    _lib.call("vt_softmax", scores.data_ptr(), probs.data_ptr(), B * num_heads * N, N, N, code, stream)
+    _lib.call("vt_gemm_strided", probs.data_ptr(), base + 2 * D * es, out.data_ptr(), None, N, dh, N, B,
+              num_heads, _lib.i64x4(num_heads * N * N, N * N, N, 1),
+              _lib.i64x4(qkv.stride(0), dh, qkv.stride(1), 1), _lib.i64x4(N * D, dh, D, 1), 1.0, 0, code,
+              stream)
+    return out

@@ -1,0 +1,91 @@
+"""Dense layer matmul — host entry point for K1 (replaces reference vit/kernels/matmul.py:111-156).
+
+Two device paths, chosen per call from dtype and alignment (one library, one architecture):
+  * bf16, K and N multiples of 8, rows of A dense  -> tcgen05/TMEM/TMA GEMM (``vt_gemm_bf16``)
+  * anything else (fp32, odd shapes, odd strides)  -> strided FP32-pipe GEMM (``vt_gemm_strided``)
+"""
+import weakref
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+# id(tensor) -> (weakref, version, derived tensor).  Only nn.Parameters are cached: a plain tensor's
+# storage can be recycled by the allocator under the same pointer, a live Parameter's cannot.
+_derived_cache = {}
+
+
+def _cached(param: torch.Tensor, tag: str, make):
+    key = (id(param), tag)
+    hit = _derived_cache.get(key)
+    if hit is not None:
+        ref, version, value = hit
+        if ref() is param and version == param._version and value.device == param.device:
+            return value
+    value = make(param)
+    if isinstance(param, torch.nn.Parameter):
+        if len(_derived_cache) > 4096:
+            _derived_cache.clear()
+        _derived_cache[key] = (weakref.ref(param), param._version, value)
+    return value
+
+
+def _k_major(B: torch.Tensor) -> torch.Tensor:
+    """(K, N) weight -> [N, K] row-major (K-major operand for the tensor core)."""
+    Bt = B.detach().t()
+    return Bt if Bt.is_contiguous() else Bt.contiguous()
+
+
+def _tensor_core_ok(A: torch.Tensor, B: torch.Tensor, N: int, K: int) -> bool:
+    if A.dtype != torch.bfloat16 or B.dtype != torch.bfloat16:
+        return False
+    if (K % 8) or (N % 8) or A.stride(2) != 1 or (A.stride(1) % 8):
+        return False
+    if A.shape[0] > 1 and A.stride(0) != A.shape[1] * A.stride(1):
+        return False
+    return A.data_ptr() % 16 == 0
+
+
+def matmul(A: torch.Tensor, B: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           activation: Optional[str] = None) -> torch.Tensor:
+    """O[b] = act(A[b] @ B + bias) with fp32 accumulation.
+
+    Args / errors follow the reference's ``matmul_triton`` (matmul.py:124-133): A is (B, T, Cin) with
+    any strides, B is (Cin, Cout), bias is (Cout,), activation is None or "gelu" (exact erf).
+    Returns a fresh (B, T, Cout) tensor in A's dtype.
+    """
+    assert len(A.shape) == 3, "First input matrix needs to have 3 dimensions (B, T, C)"
+    assert A.device == B.device and A.is_cuda, "Both matrix should be on GPU"
+    assert len(B.shape) == 2 and A.shape[2] == B.shape[0], \
+        f"Dimensions are not compatible for matrix multiplication, provided: {A.shape}, {B.shape}"
+    if bias is not None:
+        assert bias.is_cuda, "Bias is not on GPU"
+        assert bias.numel() == B.shape[1], "Bias shape does not match output feature dimension shape"
+    if activation:
+        assert activation in ["gelu"], f"Only GELU activation supported as of now! Provided: {activation}"
+
+    batch, M, K = A.shape
+    N = B.shape[1]
+    O = torch.empty((batch, M, N), device=A.device, dtype=A.dtype)
+    if O.numel() == 0:
+        return O
+    stream = _lib.stream_ptr(A)
+
+    if _tensor_core_ok(A, B, N, K):
+        Bt = _cached(B, "kmajor", _k_major)
+        bias32 = None if bias is None else _cached(bias, "f32", lambda b: b.detach().float().contiguous())
+        _lib.call("vt_gemm_bf16", A.data_ptr(), A.stride(1), Bt.data_ptr(), K, O.data_ptr(), N,
+                  _lib.VT_BF16, _lib.ptr(bias32), None, 0, batch * M, N, K, 1 if activation else 0, stream)
+        return O
+
+    assert A.dtype == B.dtype, f"Input dtypes need to be same, provided {A.dtype}, {B.dtype}"
+    if bias is not None and (bias.dtype != A.dtype or not bias.is_contiguous()):
+        bias = bias.to(A.dtype).contiguous()
+    _lib.call("vt_gemm_strided", A.data_ptr(), B.data_ptr(), O.data_ptr(), _lib.ptr(bias), M, N, K,
+              batch, 1,
+              _lib.i64x4(A.stride(0), 0, A.stride(1), A.stride(2)),
+              _lib.i64x4(0, 0, B.stride(0), B.stride(1)),
+              _lib.i64x4(M * N, 0, N, 1),
+              1.0, 1 if activation else 0, _lib.dtype_code(A), stream)
+    return O

@@ -1,0 +1,172 @@
+"""Weight packing for the fused execution path.
+
+The module tree keeps the reference's parameter layout (per-head (D, dh) query/key/value matrices,
+(in, out) dense weights — vit/vit.py:25-35,38-53; 990 state-dict keys for ViT-B).  The tensor-core
+kernels want something else: ONE K-major [3D, D] matrix for Q, K and V of all heads, K-major
+[out, in] matrices for the other dense layers, fp32 biases, and the position embedding pre-added to
+the CLS token / conv bias.  This module derives those once and caches them per module; the cache is
+dropped when the module is moved / cast (``_apply``), when a state-dict is loaded, or when any
+source parameter's storage pointer or version counter changes.
+"""
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+
+from .kernels import _lib
+
+
+class PackedMixin:
+    """Gives a module a lazily built, automatically invalidated ``packed()`` namespace."""
+
+    def _packed_sources(self):
+        return list(self.parameters())
+
+    def _packed_key(self, params):
+        return tuple((p.data_ptr(), p._version) for p in params)
+
+    def packed(self):
+        state = self.__dict__.get("_packed_state")
+        if state is not None:
+            params, key, value = state
+            if self._packed_key(params) == key:
+                return value
+        params = self._packed_sources()
+        with torch.no_grad():
+            value = self._build_packed()
+        self.__dict__["_packed_state"] = (params, self._packed_key(params), value)
+        return value
+
+    def invalidate_packed(self):
+        self.__dict__.pop("_packed_state", None)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_packed()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.invalidate_packed()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+
+def _nk(weight_in_out: torch.Tensor) -> torch.Tensor:
+    """(in, out) -> contiguous [out, in]: the K-major operand layout."""
+    return weight_in_out.detach().t().contiguous()
+
+
+def pack_attention(mha) -> SimpleNamespace:
+    heads = mha.attention
+    wq = torch.cat([h.query.weight.detach() for h in heads], dim=1)
+    wk = torch.cat([h.key.weight.detach() for h in heads], dim=1)
+    wv = torch.cat([h.value.weight.detach() for h in heads], dim=1)
+    bq = torch.cat([h.query.bias.detach() for h in heads])
+    bk = torch.cat([h.key.bias.detach() for h in heads])
+    bv = torch.cat([h.value.bias.detach() for h in heads])
+    return SimpleNamespace(
+        wqkv=_nk(torch.cat([wq, wk, wv], dim=1)),          # [3D, D]
+        bqkv=torch.cat([bq, bk, bv]).float().contiguous(),  # [3D] fp32
+        wo=_nk(mha.output.weight),                          # [D, D]
+        bo=mha.output.bias.detach().float().contiguous(),
+    )
+
+
+def pack_mlp(block) -> SimpleNamespace:
+    return SimpleNamespace(
+        w1=_nk(block.intermediate.weight),                  # [F, D]
+        b1=block.intermediate.bias.detach().float().contiguous(),
+        w2=_nk(block.output.weight),                        # [D, F]
+        b2=block.output.bias.detach().float().contiguous(),
+    )
+
+
+def pack_embeddings(emb) -> SimpleNamespace:
+    w = emb.projection.weight.detach()
+    D = w.shape[0]
+    K = w[0].numel()
+    kpad = (K + 7) // 8 * 8
+    w2d = torch.zeros((D, kpad), device=w.device, dtype=w.dtype)
+    w2d[:, :K] = w.reshape(D, K)
+    pos = emb.position_embeddings.detach().float()[0]          # [N, D]
+    posb = pos.clone()
+    posb[0] += emb.cls_token.detach().float().reshape(-1)
+    posb[1:] += emb.projection.bias.detach().float()
+    return SimpleNamespace(w=w2d, ldw=kpad, K=K, posb=posb.contiguous(),
+                           bias32=emb.projection.bias.detach().float().contiguous())
+
+
+def linear(x: torch.Tensor, w_nk: torch.Tensor, bias32: torch.Tensor, gelu: bool = False,
+           residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = epi(x @ w_nk^T + bias) over the flattened (B*N, K) activation.
+
+    bf16 -> tcgen05 GEMM with bias / GELU / residual fused into the epilogue;
+    fp32 -> exact FP32-pipe GEMM (bias / GELU fused, residual added by the add kernel).
+    """
+    B, N, K = x.shape
+    n_out = w_nk.shape[0]
+    out = torch.empty((B, N, n_out), device=x.device, dtype=x.dtype)
+    M = B * N
+    if M == 0:
+        return out
+    stream = _lib.stream_ptr(x)
+    if x.dtype == torch.bfloat16 and K % 8 == 0 and n_out % 8 == 0:
+        _lib.call("vt_gemm_bf16", x.data_ptr(), K, w_nk.data_ptr(), K, out.data_ptr(), n_out,
+                  _lib.VT_BF16, bias32.data_ptr(), _lib.ptr(residual), n_out, M, n_out, K,
+                  1 if gelu else 0, stream)
+        return out
+
+    bias = bias32 if x.dtype == torch.float32 else bias32.to(x.dtype)
+    code = _lib.dtype_code(x)
+    step = 65535 * 64
+    for m0 in range(0, M, step):
+        mm = min(step, M - m0)
+        es = x.element_size()
+        _lib.call("vt_gemm_strided", x.data_ptr() + m0 * K * es, w_nk.data_ptr(),
+                  out.data_ptr() + m0 * n_out * es, bias.data_ptr(), mm, n_out, K, 1, 1,
+                  _lib.i64x4(0, 0, K, 1), _lib.i64x4(0, 0, 1, K), _lib.i64x4(0, 0, n_out, 1),
+                  1.0, 1 if gelu else 0, code, stream)
+    if residual is not None:
+        _lib.call("vt_add", out.data_ptr(), residual.data_ptr(), out.data_ptr(), out.numel(), code, stream)
+    return out
+
+
+def patch_embed(emb, x: torch.Tensor) -> torch.Tensor:
+    """Pixels (B, C, S, S) -> token embeddings (B, n+1, D) including CLS and position embeddings."""
+    pk = emb.packed()
+    w = emb.projection.weight
+    B, C, S, _ = x.shape
+    P = emb.patch_size
+    D = emb.hidden_dim
+    n_tok = emb.num_patches + 1
+    x = x.contiguous()
+    out = torch.empty((B, n_tok, D), device=x.device, dtype=w.dtype)
+    if B == 0:
+        return out
+    stream = _lib.stream_ptr(x)
+
+    if w.dtype == torch.bfloat16 and D % 8 == 0 and x.dtype in (torch.float32, torch.bfloat16):
+        step = 65535 * 128 // emb.num_patches
+        for b0 in range(0, B, step):
+            nb = min(step, B - b0)
+            _lib.call("vt_patch_embed", x[b0:].data_ptr(), _lib.dtype_code(x), pk.w.data_ptr(), pk.ldw,
+                      pk.posb.data_ptr(), out[b0:].data_ptr(), _lib.VT_BF16, nb, C, S, P, D, stream)
+        return out
+
+    # exact path: im2col rows, strided GEMM straight into rows 1..n of every image, then CLS/pos
+    from .kernels.patching import patching
+    if x.dtype != w.dtype:
+        x = x.to(w.dtype)
+    patches = patching(x, P)
+    n = emb.num_patches
+    K = pk.K
+    code = _lib.dtype_code(out)
+    es = out.element_size()
+    bias = pk.bias32 if w.dtype == torch.float32 else emb.projection.bias.detach().contiguous()
+    for b0 in range(0, B, 32768):
+        nb = min(32768, B - b0)
+        _lib.call("vt_gemm_strided", patches[b0:].data_ptr(), pk.w.data_ptr(),
+                  out[b0:].data_ptr() + D * es, bias.data_ptr(), n, D, K, nb, 1,
+                  _lib.i64x4(n * K, 0, K, 1), _lib.i64x4(0, 0, 1, pk.ldw), _lib.i64x4(n_tok * D, 0, D, 1),
+                  1.0, 0, code, stream)
+    _lib.call("vt_embed_finalize", out.data_ptr(), emb.position_embeddings.data_ptr(),
+              emb.cls_token.data_ptr(), B, n_tok, D, code, stream)
+    return out
