@@ -1,0 +1,285 @@
+"""GPU parity of every kernel entry point against the torch op it stands for, on the reference's own
+self-check shapes plus the model shapes (197/257/577 rows, D 768/1024/1280)
+and ragged edge cases.  Tolerances are stated per test."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _seed():
+    torch.manual_seed(0)
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rel_err(got, want):
+    return ((got.float() - want.float()).norm() / want.float().norm().clamp_min(1e-12)).item()
+
+
+# ------------------------------------------------------------------------------- layernorm (K4)
+@pytest.mark.parametrize("shape", [(2, 25, 50), (4, 197, 768), (2, 257, 1280), (1, 577, 1024), (3, 7, 8), (1, 1, 4100)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_layernorm(shape, dtype):
+    from vit.kernels import layernorm
+    x = torch.randn(shape, device=dev()).to(dtype)
+    w = (1 + 0.1 * torch.randn(shape[-1], device=dev())).to(dtype)
+    b = (0.1 * torch.randn(shape[-1], device=dev())).to(dtype)
+    got = layernorm(x, w, b, 1e-12)
+    want = F.layer_norm(x.float(), (shape[-1],), w.float(), b.float(), 1e-12)
+    assert got.dtype == dtype and got.shape == x.shape
+    if dtype == torch.float32:
+        assert (got - want).abs().max().item() <= 2e-5      # reference self-check: atol 1e-6 at (2,25,50)
+    else:
+        assert (got.float() - want).abs().max().item() <= 4e-2 and rel_err(got, want) <= 2 ** -7
+
+
+def test_layernorm_module_and_mixed_output():
+    from vit.kernels import LayerNormTriton, layernorm
+    ln = LayerNormTriton(768, eps=1e-12).to(dev())
+    x = torch.randn(2, 197, 768, device=dev())
+    want = F.layer_norm(x, (768,), ln.weight, ln.bias, 1e-12)
+    assert (ln(x) - want).abs().max().item() <= 2e-5
+    got = layernorm(x, ln.weight.data, ln.bias.data, 1e-12, out_dtype=torch.bfloat16)
+    assert got.dtype == torch.bfloat16 and rel_err(got, want) <= 2 ** -7
+
+
+# ------------------------------------------------------------------------------- add (K5)
+@pytest.mark.parametrize("shape", [(2, 2000, 5000), (4, 197, 768), (1, 3, 5), (1, 1, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_add(shape, dtype):
+    from vit.kernels import add
+    a = torch.randn(shape, device=dev()).to(dtype)
+    b = torch.randn(shape, device=dev()).to(dtype)
+    got = add(a, b)
+    assert torch.equal(got, a + b)       # one rounding of an exact fp32 sum: bit-exact with torch
+
+
+def test_add_rejects_bad_inputs():
+    from vit.kernels import add
+    a = torch.randn(2, 4, 8, device=dev())
+    with pytest.raises(AssertionError):
+        add(a, torch.randn(2, 4, 4, device=dev()))
+    with pytest.raises(AssertionError):
+        add(a.transpose(1, 2), a.transpose(1, 2))
+    with pytest.raises(AssertionError):
+        add(a[0], a[0])
+
+
+# ------------------------------------------------------------------------------- softmax (K6)
+@pytest.mark.parametrize("shape", [(1, 1823, 781), (12, 197, 197), (2, 577, 577), (1, 1, 1), (2, 3, 33)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_softmax(shape, dtype):
+    from vit.kernels import softmax
+    x = torch.randint(0, 10, shape, device=dev()).to(dtype) if shape[1] == 1823 else (3 * torch.randn(shape, device=dev())).to(dtype)
+    got = softmax(x)
+    want = torch.softmax(x.float(), dim=-1)
+    tol = 1e-6 if dtype == torch.float32 else 4e-3
+    assert (got.float() - want).abs().max().item() <= tol
+
+
+# ------------------------------------------------------------------------------- matmul (K1 + exact path)
+@pytest.mark.parametrize("shape", [((4, 20, 30), (30, 10)), ((1, 197, 768), (768, 64)), ((2, 65, 129), (129, 77))])
+@pytest.mark.parametrize("act", [None, "gelu"])
+def test_matmul_fp32_exact(shape, act):
+    from vit.kernels import matmul
+    a = torch.randn(shape[0], device=dev())
+    b = torch.randn(shape[1], device=dev())
+    bias = torch.randn(shape[1][1], device=dev())
+    got = matmul(a, b, bias, act)
+    want = a.double() @ b.double() + bias.double()
+    if act:
+        want = F.gelu(want)
+    assert (got.double() - want).abs().max().item() <= 1e-4 * max(1.0, math.sqrt(shape[1][0]) / 4)
+
+
+def test_matmul_fp32_strided_input():
+    from vit.kernels import matmul
+    a = torch.randn(3, 40, 24, device=dev()).transpose(1, 2)       # (3, 24, 40), non-contiguous
+    b = torch.randn(64, 40, device=dev()).t()                       # (40, 64), non-contiguous
+    got = matmul(a, b)
+    assert (got - a @ b).abs().max().item() <= 1e-4
+
+
+GEMM_SHAPES = [
+    (197, 768, 2304), (197 * 8, 768, 768), (197 * 8, 768, 3072), (197 * 4, 3072, 768),   # ViT-B layers
+    (128, 64, 128), (1, 768, 768), (300, 264, 40), (129, 72, 264), (513, 1280, 1280),     # ragged M/N/K
+]
+
+
+@pytest.mark.parametrize("M,K,N", GEMM_SHAPES)
+@pytest.mark.parametrize("act", [None, "gelu"])
+def test_matmul_bf16_tensor_core(M, K, N, act):
+    from vit.kernels import matmul
+    a = torch.randn(1, M, K, device=dev()).bfloat16()
+    w = (torch.randn(K, N, device=dev()) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=dev()).bfloat16()
+    got = matmul(a, w, bias, act)
+    want = a.float() @ w.float() + bias.float()
+    if act:
+        want = F.gelu(want)
+    assert got.dtype == torch.bfloat16 and got.shape == (1, M, N)
+    assert rel_err(got, want) <= 2 ** -7, f"rel err {rel_err(got, want)}"
+    assert (got.float() - want).abs().max().item() <= 0.06
+
+
+@pytest.mark.parametrize("M,K,N", [(197 * 6, 768, 768), (77, 3072, 768), (1000, 128, 136)])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_gemm_bf16_residual_epilogue(M, K, N, out_dtype):
+    from vit import packing
+    from vit.kernels import _lib
+    x = torch.randn(1, M, K, device=dev()).bfloat16()
+    w_nk = (torch.randn(N, K, device=dev()) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=dev())
+    res = torch.randn(1, M, N, device=dev()).to(out_dtype)
+    want = x.float() @ w_nk.float().t() + bias + res.float()
+    if out_dtype == torch.bfloat16:
+        got = packing.linear(x, w_nk, bias, residual=res)
+    else:
+        got = torch.empty(1, M, N, device=dev(), dtype=torch.float32)
+        _lib.call("vt_gemm_bf16", x.data_ptr(), K, w_nk.data_ptr(), K, got.data_ptr(), N, _lib.VT_F32,
+                  bias.data_ptr(), res.data_ptr(), N, M, N, K, 0, _lib.stream_ptr(x))
+    tol = 2 ** -7 if out_dtype == torch.bfloat16 else 1e-5
+    assert rel_err(got, want) <= tol, f"rel err {rel_err(got, want)}"
+
+
+def test_gemm_bf16_in_place_residual():
+    from vit.kernels import _lib
+    M, K, N = 197 * 3, 768, 768
+    x = torch.randn(M, K, device=dev()).bfloat16()
+    w_nk = (torch.randn(N, K, device=dev()) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=dev())
+    res = torch.randn(M, N, device=dev()).bfloat16()
+    want = x.float() @ w_nk.float().t() + bias + res.float()
+    _lib.call("vt_gemm_bf16", x.data_ptr(), K, w_nk.data_ptr(), K, res.data_ptr(), N, _lib.VT_BF16,
+              bias.data_ptr(), res.data_ptr(), N, M, N, K, 0, _lib.stream_ptr(x))
+    assert rel_err(res, want) <= 2 ** -7
+
+
+def test_gemm_bf16_rejects_misaligned():
+    from vit.kernels import _lib
+    x = torch.randn(16, 12, device=dev()).bfloat16()
+    w = torch.randn(16, 12, device=dev()).bfloat16()
+    out = torch.empty(16, 16, device=dev()).bfloat16()
+    with pytest.raises(_lib.KernelError):
+        _lib.call("vt_gemm_bf16", x.data_ptr(), 12, w.data_ptr(), 12, out.data_ptr(), 16, _lib.VT_BF16,
+                  None, None, 0, 16, 16, 12, 0, _lib.stream_ptr(x))
+
+
+# ------------------------------------------------------------------------------- matmul3
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-2), (torch.bfloat16, 0.5)])
+def test_matmul3(dtype, tol):
+    from vit.kernels import matmul3
+    a = torch.randn(4, 120, 760, device=dev()).to(dtype)
+    b = torch.randn(4, 760, 500, device=dev()).to(dtype)
+    got = matmul3(a, b, apply_scaling=True, scale_factor=1 / math.sqrt(760))
+    want = (a.float() @ b.float()) / math.sqrt(760)
+    assert (got.float() - want).abs().max().item() <= (1e-4 if dtype == torch.float32 else 0.03)
+    assert torch.equal(matmul3(a[:1, :3], b[:1, :, :2]), matmul3(a[:1, :3].contiguous(), b[:1, :, :2].contiguous()))
+
+
+# ------------------------------------------------------------------------------- attention (K3)
+def _attn_ref(qkv, H):
+    B, N, D3 = qkv.shape
+    D = D3 // 3
+    dh = D // H
+    q, k, v = qkv.float().split(D, dim=2)
+    q = q.view(B, N, H, dh).transpose(1, 2)
+    k = k.view(B, N, H, dh).transpose(1, 2)
+    v = v.view(B, N, H, dh).transpose(1, 2)
+    p = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), dim=-1)
+    return (p @ v).transpose(1, 2).reshape(B, N, D)
+
+
+@pytest.mark.parametrize("B,H,N", [(2, 12, 197), (1, 2, 17), (1, 1, 128), (1, 1, 129), (2, 3, 256), (1, 16, 257), (2, 12, 577), (1, 1, 1), (1, 2, 16)])
+def test_flash_attention_bf16(B, H, N):
+    from vit.kernels import flash_attention
+    qkv = torch.randn(B, N, 3 * H * 64, device=dev()).bfloat16()
+    got = flash_attention(qkv, H)
+    want = _attn_ref(qkv, H)
+    assert got.shape == (B, N, H * 64) and got.dtype == torch.bfloat16
+    assert torch.isfinite(got.float()).all()
+    assert (got.float() - want).abs().max().item() <= 2e-2, f"max err {(got.float() - want).abs().max().item()}"
+    assert rel_err(got, want) <= 1e-2
+
+
+def test_flash_attention_peaky_scores():
+    """Large logits: the online max subtraction must keep exp() in range."""
+    from vit.kernels import flash_attention
+    qkv = (8 * torch.randn(1, 577, 3 * 2 * 64, device=dev())).bfloat16()
+    got = flash_attention(qkv, 2)
+    want = _attn_ref(qkv, 2)
+    assert torch.isfinite(got.float()).all()
+    assert rel_err(got, want) <= 2e-2
+
+
+@pytest.mark.parametrize("dtype,H,dh", [(torch.float32, 2, 64), (torch.float32, 2, 80), (torch.bfloat16, 2, 80)])
+def test_attention_exact_path(dtype, H, dh):
+    from vit.kernels import flash_attention
+    qkv = torch.randn(2, 57, 3 * H * dh, device=dev()).to(dtype)
+    got = flash_attention(qkv, H)
+    D = H * dh
+    q, k, v = qkv.float().split(D, dim=2)
+    sh = lambda t: t.view(2, 57, H, dh).transpose(1, 2)
+    want = (torch.softmax(sh(q) @ sh(k).transpose(-1, -2) / math.sqrt(dh), -1) @ sh(v)).transpose(1, 2).reshape(2, 57, D)
+    assert (got.float() - want).abs().max().item() <= (1e-5 if dtype == torch.float32 else 3e-2)
+
+
+# ------------------------------------------------------------------------------- conv2d / patching / patch-embed (K2)
+def test_patching_matches_unfold():
+    from vit.kernels import patching
+    img = torch.arange(2 * 3 * 32 * 32, device=dev(), dtype=torch.float32).view(2, 3, 32, 32)
+    got = patching(img, 16)
+    want = img.unfold(2, 16, 16).unfold(3, 16, 16).permute(0, 2, 3, 1, 4, 5).contiguous().view(2, -1, 3 * 256)
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("kshape", [(512, 3, 16, 16), (40, 3, 14, 14), (8, 3, 4, 2)])
+def test_conv2d_fp32(kshape):
+    from vit.kernels import conv2d, Conv2DTriton
+    x = torch.randint(0, 10, (4, 3, 224, 224), device=dev()).float()
+    w = torch.randn(kshape, device=dev()) * 0.05
+    b = torch.randn(kshape[0], device=dev())
+    got = conv2d(x, w, b)
+    want = F.conv2d(x.double(), w.double(), b.double(), stride=kshape[2:]).float()
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() <= 2e-3
+    mod = Conv2DTriton(3, kshape[0], tuple(kshape[2:])).to(dev())
+    with torch.no_grad():
+        mod.weight.copy_(w)
+        mod.bias.copy_(b)
+    assert torch.equal(mod(x), got)
+
+
+@pytest.mark.parametrize("S,P,D,B", [(224, 16, 768, 3), (384, 16, 768, 1), (224, 14, 1280, 2), (64, 16, 128, 5), (56, 14, 160, 2)])
+@pytest.mark.parametrize("pix_dtype", [torch.float32, torch.bfloat16])
+def test_patch_embed_fused(S, P, D, B, pix_dtype):
+    from vit.vit import Embeddings
+    n = (S // P) ** 2
+    emb = Embeddings(P, n, 3 * P * P, D).to(dev())
+    with torch.no_grad():
+        for p_ in emb.parameters():
+            p_.copy_(torch.randn_like(p_) * 0.05)
+    emb = emb.to(torch.bfloat16)
+    x = torch.randn(B, 3, S, S, device=dev()).to(pix_dtype)
+    got = emb(x)
+    xb = x.bfloat16().float()
+    tok = F.conv2d(xb, emb.projection.weight.float(), emb.projection.bias.float(), stride=P).flatten(2).transpose(1, 2)
+    want = torch.cat([emb.cls_token.float().expand(B, -1, -1), tok], 1) + emb.position_embeddings.float()
+    assert got.shape == (B, n + 1, D) and got.dtype == torch.bfloat16
+    assert rel_err(got, want) <= 2 ** -7, f"rel err {rel_err(got, want)}"
+    assert (got.float() - want).abs().max().item() <= 0.05
+
+
+def test_pool_cls():
+    from vit.kernels import _lib
+    x = torch.randn(5, 197, 768, device=dev()).bfloat16()
+    out = torch.empty(5, 768, device=dev(), dtype=torch.bfloat16)
+    _lib.call("vt_pool_cls", x.data_ptr(), out.data_ptr(), 5, 768, x.stride(0), _lib.VT_BF16, _lib.stream_ptr(x))
+    assert torch.equal(out, x[:, 0, :])
