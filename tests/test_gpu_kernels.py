@@ -181,7 +181,8 @@ def test_matmul3(dtype, tol):
     got = matmul3(a, b, apply_scaling=True, scale_factor=1 / math.sqrt(760))
     want = (a.float() @ b.float()) / math.sqrt(760)
     assert (got.float() - want).abs().max().item() <= (1e-4 if dtype == torch.float32 else 0.03)
-    assert torch.equal(matmul3(a[:1, :3], b[:1, :, :2]), matmul3(a[:1, :3].contiguous(), b[:1, :, :2].contiguous()))
+    with pytest.raises(AssertionError):
+        matmul3(a[:1, :3], b[:1, :, :2])       # non-contiguous second operand, like the reference
 
 
 # ------------------------------------------------------------------------------- attention (K3)

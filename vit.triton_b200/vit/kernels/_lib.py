@@ -104,9 +104,18 @@ def i64x4(a, b, c, d):
 # Count of kernel launches issued through this module (bench.py reports it as gpu_launches).
 launch_count = 0
 
+# Optional profiling hook: event_hook(name, before: bool) is called on the launching thread right
+# before and right after a kernel is enqueued (bench.py records CUDA events there).
+event_hook = None
+
 
 def call(name: str, *args) -> None:
     global launch_count
+    hook = event_hook
+    if hook is not None:
+        hook(name, True)
     rc = getattr(load(), name)(*args)
+    if hook is not None:
+        hook(name, False)
     launch_count += 1
     check(rc, name)
