@@ -2,6 +2,7 @@
 // only, all kernels live in the other translation units.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/vitb200.h"
 
@@ -13,6 +14,8 @@ int softmax_rows(const void*, void*, long long, int, long long, int, cudaStream_
 int pool_cls(const void*, void*, int, int, long long, int, cudaStream_t);
 int gemm_bf16_tcgen05(const void*, long long, const void*, long long, void*, long long, int,
                       const float*, const void*, long long, int, int, int, int, cudaStream_t);
+int gemm2_bf16_tcgen05(const void*, long long, const void*, long long, void*, long long, const float*,
+                       const void*, long long, int, int, int, int, cudaStream_t);
 int simt_gemm(const void*, const void*, void*, const void*, int, int, int, int, int,
               const long long*, const long long*, const long long*, float, int, int, cudaStream_t);
 int attn_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
@@ -64,6 +67,15 @@ int vt_softmax(const void* x, void* out, int64_t rows, int32_t cols, int64_t in_
 int vt_gemm_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, void* out, int64_t ldo,
                  int32_t out_dtype, const float* bias, const void* residual, int64_t ldr,
                  int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream) {
+  // bf16 output -> 2-CTA kernel (gemm2_sm100.cu); fp32 output -> 1-CTA kernel (gemm_sm100.cu).
+  // VT_GEMM_IMPL=1 forces the 1-CTA kernel (A/B measurements only).
+  static const int impl = [] {
+    const char* e = getenv("VT_GEMM_IMPL");
+    return (e && e[0] == '1') ? 1 : 2;
+  }();
+  if (out_dtype == VT_BF16 && impl == 2)
+    return vt::gemm2_bf16_tcgen05(A, lda, Bt, ldb, out, ldo, bias, residual, ldr, M, N, K, gelu,
+                                  S(stream));
   return vt::gemm_bf16_tcgen05(A, lda, Bt, ldb, out, ldo, out_dtype, bias, residual, ldr, M, N, K,
                                gelu, S(stream));
 }

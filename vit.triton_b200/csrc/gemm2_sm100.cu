@@ -1,0 +1,424 @@
+// K1 (main variant): persistent 2-CTA bf16 GEMM — tcgen05.mma.cta_group::2 on a CTA pair.
+//
+//   out[M,N] = epilogue( A[M,K] . Bt[N,K]^T + bias[N] ) (+ residual[M,N]),  bf16 in / bf16 out
+//
+// Same contract as gemm_sm100.cu (which stays as the fp32-output / fallback variant); this one is
+// what the bf16 model runs.  Reference ops replaced: matmul_kernel (vit/kernels/matmul.py:40-108)
+// with its bias / GELU epilogue, and add_kernel (vit/vit.py:140,147) via the residual epilogue.
+//
+// A cluster of two CTAs (one TPC) owns a 256 x 256 output tile: CTA r holds rows [128r, 128r+128)
+// of the tile in its TMEM (128 lanes x 256 fp32 columns, double buffered = all 512 columns) and
+// loads A rows [128r, +128) and Bt rows [128r, +128) of every 64-wide K block, so each SM pulls
+// 32 KB per K block from L2 instead of 48 KB for the same number of MACs.  Only the leader CTA
+// issues MMAs (M=256, N=256, K=16); both CTAs' TMA loads complete on the leader's mbarrier.
+//
+// Epilogue: 8 warps per CTA; warp (q, h) owns TMEM lanes 32q..32q+31 and columns 128h..128h+127.
+// Per 64-column chunk: tcgen05.ld -> +bias -> (+residual from smem) -> (GELU) -> bf16 ->
+// SWIZZLE_128B staging buffer -> TMA store.  The residual chunk is TMA-LOADED into the same staging
+// buffer before the accumulator is ready, so neither residual reads nor output writes go through
+// per-thread global accesses (the v1 row-per-thread stores made the epilogue the bottleneck:
+// profiles/r01_*).
+#include "common.cuh"
+#include "tensormap.h"
+
+namespace vt {
+
+namespace {
+
+constexpr int BM = 128;          // rows per CTA (pair tile = 256)
+constexpr int BN = 256;          // tile columns
+constexpr int BNH = 128;         // Bt rows loaded per CTA
+constexpr int BK = 64;
+constexpr int kStages = 5;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + kEpiWarps * 32;
+constexpr int kABytes = BM * BK * 2;
+constexpr int kBBytes = BNH * BK * 2;
+constexpr int kStageBytes = kABytes + kBBytes;          // 32 KB
+constexpr int kChunkCols = 64;
+constexpr int kStagingBytes = 32 * kChunkCols * 2;      // 4 KB: 32 rows x 64 bf16
+constexpr int kEpiBytes = kEpiWarps * 2 * kStagingBytes; // 64 KB
+constexpr int kNumBars = 2 * kStages + 4 + 2 * kEpiWarps;
+constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiBytes + 8 * kNumBars + 16;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;             // clears the CTA-rank bit of a cluster smem address
+
+enum : int { EPI_GELU = 1, EPI_RES = 2 };
+
+struct Gemm2Params {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles;   // in units of the 256 x 256 pair tile
+  const float* bias;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t num_clusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+               "n"(kCols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols)
+               : "memory");
+}
+
+// TMA load whose completion bytes are credited to the mbarrier at the same offset in the LEADER CTA.
+__device__ __forceinline__ void tma_load_2d_2cta(const CUtensorMap* m, uint32_t bar, uint32_t dst,
+                                                 int c0, int c1, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerMask), "r"(c0), "r"(c1),
+        "l"(hint)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Arrive (once all prior MMAs of this thread completed) on the barrier at this offset in BOTH CTAs.
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;"
+      :
+      : "r"(bar), "h"(mask)
+      : "memory");
+}
+
+// Arrive on the barrier at this offset in the leader CTA (works from either CTA of the pair).
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
+}
+
+__device__ __forceinline__ float gelu_epi(float x) { return gelu_erf(x); }
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                  const __grid_constant__ CUtensorMap tma_out,
+                  const __grid_constant__ CUtensorMap tma_res, const Gemm2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const uint32_t tiles_addr = smem_base;
+  const uint32_t epi_addr = smem_base + kStages * kStageBytes;
+  const uint32_t bar_addr = epi_addr + kEpiBytes;
+  auto full_bar = [&](int s) { return bar_addr + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_addr + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_addr + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_addr + 8u * (2 * kStages + 2 + s); };
+  auto res_bar = [&](int w, int c) { return bar_addr + 8u * (2 * kStages + 4 + 2 * w + c); };
+  const uint32_t tmem_slot = bar_addr + 8u * kNumBars;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + kStages * kStageBytes + kEpiBytes + 8 * kNumBars);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool is_leader = (cta_rank == 0);
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_out);
+    if (EPI & EPI_RES) tma_prefetch_desc(&tma_res);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);      // leader's producer arrive.expect_tx (covers both CTAs' bytes)
+      mbar_init(empty_bar(s), 1);     // multicast tcgen05.commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);                 // multicast tcgen05.commit
+      mbar_init(tempty_bar(s), 2 * kEpiWarps);    // epilogue warps of BOTH CTAs (leader's copy is used)
+    }
+    for (int w = 0; w < kEpiWarps; ++w) {
+      mbar_init(res_bar(w, 0), 1);
+      mbar_init(res_bar(w, 1), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc_2cta<512>(tmem_slot);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int first_tile = static_cast<int>(cluster_id_x());
+  const int tile_step = static_cast<int>(num_clusters_x());
+
+  if (warp_idx == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int s = 0;
+      uint32_t phase = 0;
+      for (int t = first_tile; t < num_tiles; t += tile_step) {
+        const int m_blk = t / p.num_n_tiles;
+        const int n_blk = t - m_blk * p.num_n_tiles;
+        const int a_row = m_blk * (2 * BM) + static_cast<int>(cta_rank) * BM;
+        const int b_row = n_blk * BN + static_cast<int>(cta_rank) * BNH;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(s), phase ^ 1u);
+          const uint32_t a_dst = tiles_addr + s * kStageBytes;
+          const uint32_t b_dst = a_dst + kABytes;
+          if (is_leader) mbar_arrive_expect_tx(full_bar(s), 2 * kStageBytes);
+          tma_load_2d_2cta(&tma_a, full_bar(s), a_dst, kb * BK, a_row, kEvictNormal);
+          tma_load_2d_2cta(&tma_b, full_bar(s), b_dst, kb * BK, b_row, kEvictLast);
+          if (++s == kStages) { s = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader only)
+    if (is_leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+      int s = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = first_tile; t < num_tiles; t += tile_step) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(s), phase);
+          tc_fence_after();
+          const uint32_t a_src = tiles_addr + s * kStageBytes;
+          const uint32_t b_src = a_src + kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_ss_2cta(d_tmem, make_desc_kmajor_sw128(a_src + k * 32),
+                         make_desc_kmajor_sw128(b_src + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2cta(empty_bar(s));
+          if (++s == kStages) { s = 0; phase ^= 1u; }
+        }
+        umma_commit_2cta(tfull_bar(as));
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ------------------------------------------------------------------ epilogue (both CTAs)
+    const int ew = warp_idx - 4;
+    const int q = warp_idx & 3;
+    const int half = ew >> 2;
+    const uint32_t stage_buf[2] = {epi_addr + (2 * ew + 0) * kStagingBytes,
+                                   epi_addr + (2 * ew + 1) * kStagingBytes};
+    uint8_t* stage_gen[2] = {smem_gen + kStages * kStageBytes + (2 * ew + 0) * kStagingBytes,
+                             smem_gen + kStages * kStageBytes + (2 * ew + 1) * kStagingBytes};
+    const int sw = lane & 7;   // swizzle phase of this thread's staging row
+    int as = 0;
+    uint32_t aphase = 0;
+    uint32_t rphase = 0;
+    for (int t = first_tile; t < num_tiles; t += tile_step) {
+      const int m_blk = t / p.num_n_tiles;
+      const int n_blk = t - m_blk * p.num_n_tiles;
+      const int row0 = m_blk * (2 * BM) + static_cast<int>(cta_rank) * BM + q * 32;
+      const int col0 = n_blk * BN + half * 128;
+
+      if (EPI & EPI_RES) {
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            mbar_arrive_expect_tx(res_bar(ew, c), kStagingBytes);
+            tma_load_2d(&tma_res, res_bar(ew, c), stage_buf[c], col0 + c * kChunkCols, row0,
+                        kEvictFirst);
+          }
+        }
+      }
+
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + half * 128;
+
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(t_addr + c * kChunkCols, r0);
+        tmem_ld_32x32(t_addr + c * kChunkCols + 32, r1);
+        tmem_ld_wait();
+        if (c == 1) {
+          // accumulator fully read: hand the TMEM stage back to the MMA issuer before the math
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(tempty_bar(as));
+        }
+        const int col = col0 + c * kChunkCols;
+        if (col < p.N) {   // warp-uniform
+          if (EPI & EPI_RES) mbar_wait(res_bar(ew, c), rphase);
+          uint8_t* rowp = stage_gen[c] + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            // 8 consecutive columns: col + 8j .. col + 8j + 7
+            const uint32_t* rr = (j < 4) ? &r0[8 * j] : &r1[8 * (j - 4)];
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(rr[e]);
+            if (p.bias != nullptr) {
+              const int cb = col + 8 * j;
+              float4 b0, b1;
+              if (cb + 7 < p.N) {
+                b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cb));
+                b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + 4));
+              } else {
+                b0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                b1 = b0;   // N is a multiple of 8: a partial group of 8 cannot occur, only a fully OOB one
+              }
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            uint4* slot = reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4));
+            if (EPI & EPI_RES) {
+              const uint4 r4 = *slot;
+              v[0] += bf16_lo(r4.x); v[1] += bf16_hi(r4.x);
+              v[2] += bf16_lo(r4.y); v[3] += bf16_hi(r4.y);
+              v[4] += bf16_lo(r4.z); v[5] += bf16_hi(r4.z);
+              v[6] += bf16_lo(r4.w); v[7] += bf16_hi(r4.w);
+            }
+            if (EPI & EPI_GELU) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = gelu_epi(v[e]);
+            }
+            uint4 o4;
+            o4.x = pack_bf16x2(v[0], v[1]);
+            o4.y = pack_bf16x2(v[2], v[3]);
+            o4.z = pack_bf16x2(v[4], v[5]);
+            o4.w = pack_bf16x2(v[6], v[7]);
+            *slot = o4;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tma_out, stage_buf[c], col, row0);
+            tma_store_commit();
+          }
+        } else if (EPI & EPI_RES) {
+          mbar_wait(res_bar(ew, c), rphase);   // keep the barrier phase in step (load was all-OOB)
+        }
+      }
+      // staging buffers must be drained (read by the TMA engine) before the next tile reuses them
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+      rphase ^= 1u;
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta<512>(tmem_base);
+  }
+}
+
+int g_num_sms2 = 0;
+int num_sms2() {
+  if (g_num_sms2 == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms2, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms2 <= 0) g_num_sms2 = 148;
+  }
+  return g_num_sms2;
+}
+
+template <int EPI>
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+            const CUtensorMap& tr, const Gemm2Params& p, cudaStream_t stream) {
+  auto kern = gemm2_bf16_kernel<EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  int clusters = num_sms2() / 2;
+  if (tiles < clusters) clusters = tiles;
+  kern<<<2 * clusters, kThreads, kSmemBytes, stream>>>(ta, tb, to, tr, p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace
+
+// bf16 in / bf16 out 2-CTA GEMM.  Same argument meaning as gemm_bf16_tcgen05 (out dtype fixed).
+int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long ldb, void* out,
+                       long long ldo, const float* bias, const void* residual, long long ldr, int M,
+                       int N, int K, int gelu, cudaStream_t stream) {
+  if (!A || !Bt || !out || M <= 0 || N <= 0 || K <= 0) return VT_ERR_ARG;
+  if (gelu && residual) return VT_ERR_UNSUPPORTED;
+  if ((K % 8) || (lda % 8) || (ldb % 8) || (N % 8) || (ldo % 8) || (residual && (ldr % 8)))
+    return VT_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bt) |
+       reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(residual) |
+       reinterpret_cast<uintptr_t>(bias)) & 15)
+    return VT_ERR_ALIGN;
+
+  CUtensorMap ta, tb, to, tr;
+  int rc = make_tmap_bf16_2d(&ta, A, K, M, lda, BK, BM, TMAP_SW_128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tb, Bt, K, N, ldb, BK, BNH, TMAP_SW_128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&to, out, N, M, ldo, kChunkCols, 32, TMAP_SW_128);
+  if (rc) return rc;
+  if (residual) {
+    rc = make_tmap_bf16_2d(&tr, residual, N, M, ldr, kChunkCols, 32, TMAP_SW_128);
+    if (rc) return rc;
+  } else {
+    tr = to;
+  }
+
+  Gemm2Params p;
+  p.M = M; p.N = N; p.K = K;
+  p.num_m_tiles = (M + 2 * BM - 1) / (2 * BM);
+  p.num_n_tiles = (N + BN - 1) / BN;
+  p.bias = bias;
+  if (gelu) return launch2<EPI_GELU>(ta, tb, to, tr, p, stream);
+  if (residual) return launch2<EPI_RES>(ta, tb, to, tr, p, stream);
+  return launch2<0>(ta, tb, to, tr, p, stream);
+}
+
+}  // namespace vt
