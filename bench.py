@@ -171,7 +171,7 @@ def run_reference(args, arch, desc):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
@@ -248,12 +248,12 @@ def main():
             gemm_events.append(ev)
 
     with torch.no_grad():
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()          # nvidia-smi needs ~0.5 s to produce its first sample
         for i in range(args.warmup):
             step(dev_inputs[i % n_rot])
         sync_all()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         launches0 = _lib.launch_count
         _lib.event_hook = hook
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -92,7 +92,7 @@ def fam_gemm():
     # timing at C2 layer shapes
     from vit.kernels import _lib
     M = 256 * 197
-    for (K, N, act, res) in ((768, 2304, 0, False), (768, 768, 0, True), (768, 3072, 1, False), (3072, 768, 0, True)):
+    for (K, N, act, res) in ((768, 2304, 0, False), (768, 768, 0, True), (768, 768, 0, False), (768, 3072, 1, False), (768, 3072, 0, False), (3072, 768, 0, True), (3072, 768, 0, False)):
         x = torch.randn(M, K, device="cuda").bfloat16()
         w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
         bias = torch.randn(N, device="cuda")
@@ -105,11 +105,11 @@ def fam_gemm():
             run()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        for _ in range(10):
+        for _ in range(50):
             run()
         e.record()
         torch.cuda.synchronize()
-        ms = s.elapsed_time(e) / 10
+        ms = s.elapsed_time(e) / 50
         print(f"gemm C2 K={K} N={N} gelu={act} res={res}: {ms*1e3:.1f} us  {2*M*N*K/ms/1e9:.0f} TFLOP/s")
 
 

@@ -16,6 +16,7 @@ int gemm_bf16_tcgen05(const void*, long long, const void*, long long, void*, lon
                       const float*, const void*, long long, int, int, int, int, cudaStream_t);
 int gemm2_bf16_tcgen05(const void*, long long, const void*, long long, void*, long long, const float*,
                        const void*, long long, int, int, int, int, cudaStream_t);
+void gemm2_set_debug_buffer(void*);
 int simt_gemm(const void*, const void*, void*, const void*, int, int, int, int, int,
               const long long*, const long long*, const long long*, float, int, int, cudaStream_t);
 int attn_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
@@ -33,6 +34,9 @@ static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 extern "C" {
 
 int vt_version(void) { return 100; }
+
+// Developer hook (not part of the public header): per-CTA cycle counters of the 2-CTA GEMM.
+void vt_debug_set_buffer(void* ptr) { vt::gemm2_set_debug_buffer(ptr); }
 
 const char* vt_status_string(int status) {
   switch (status) {

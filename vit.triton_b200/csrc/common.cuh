@@ -316,6 +316,38 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
+// Exact-erf GELU to 3.3e-7 absolute (Abramowitz-Stegun 7.1.26 for erfc, two MUFU ops + 12 FMA-pipe
+// ops): gelu(x) = relu(x) - 0.5|x| * P(t) * exp(-x^2/2), t = 1/(1 + p|x|/sqrt(2)).  Used where the
+// result is rounded to bf16 (rounding error >= 2e-3 relative); fp32 outputs use erff.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(ax, 0.23164189f, 1.0f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752f));
+  return fmaxf(x, 0.0f) - (0.5f * ax) * poly * e;
+}
+
+// GELU for results that are immediately rounded to bf16: the 3-term Abramowitz-Stegun 7.1.25 erfc
+// (|erf error| <= 2.5e-5, |gelu error| <= 2.6e-5 absolute, i.e. 1/75 of a bf16 ulp at |x| ~ 1) in 11
+// instructions, two of them MUFU.  Coefficients are pre-multiplied by 0.5.
+__device__ __forceinline__ float gelu_erf_bf16(float x) {
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(ax, 0.33267253f, 1.0f)));
+  float poly = fmaf(t, 0.3739278f, -0.0479399f);
+  poly = fmaf(t, poly, 0.1740121f);
+  const float h = (poly * t) * ax;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752f));
+  return fmaf(-h, e, fmaxf(x, 0.0f));
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

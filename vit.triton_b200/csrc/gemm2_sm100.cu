@@ -12,7 +12,8 @@
 // 32 KB per K block from L2 instead of 48 KB for the same number of MACs.  Only the leader CTA
 // issues MMAs (M=256, N=256, K=16); both CTAs' TMA loads complete on the leader's mbarrier.
 //
-// Epilogue: 8 warps per CTA; warp (q, h) owns TMEM lanes 32q..32q+31 and columns 128h..128h+127.
+// Epilogue: 8 warps per CTA; warp (q, g) owns TMEM lanes 32q..32q+31 and columns 128g..128g+127
+// (16 warps x 64 columns measured no faster: the GELU epilogue is not latency-bound).
 // Per 64-column chunk: tcgen05.ld -> +bias -> (+residual from smem) -> (GELU) -> bf16 ->
 // SWIZZLE_128B staging buffer -> TMA store.  The residual chunk is TMA-LOADED into the same staging
 // buffer before the accumulator is ready, so neither residual reads nor output writes go through
@@ -30,15 +31,21 @@ constexpr int BN = 256;          // tile columns
 constexpr int BNH = 128;         // Bt rows loaded per CTA
 constexpr int BK = 64;
 constexpr int kStages = 5;
-constexpr int kEpiWarps = 8;
+#ifndef VT_EPI_WARPS
+#define VT_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = VT_EPI_WARPS;            // 4 lane quarters x (2 | 4) column groups
+constexpr int kColGroups = kEpiWarps / 4;
+constexpr int kColsPerWarp = BN / kColGroups;       // 64
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kABytes = BM * BK * 2;
 constexpr int kBBytes = BNH * BK * 2;
 constexpr int kStageBytes = kABytes + kBBytes;          // 32 KB
 constexpr int kChunkCols = 64;
 constexpr int kStagingBytes = 32 * kChunkCols * 2;      // 4 KB: 32 rows x 64 bf16
-constexpr int kEpiBytes = kEpiWarps * 2 * kStagingBytes; // 64 KB
-constexpr int kNumBars = 2 * kStages + 4 + 2 * kEpiWarps;
+constexpr int kChunks = kColsPerWarp / kChunkCols;          // staging buffers (= chunks) per warp
+constexpr int kEpiBytes = kEpiWarps * kChunks * kStagingBytes; // 64 KB
+constexpr int kNumBars = 2 * kStages + 4 + kChunks * kEpiWarps;
 constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiBytes + 8 * kNumBars + 16;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;             // clears the CTA-rank bit of a cluster smem address
 
@@ -48,6 +55,7 @@ struct Gemm2Params {
   int M, N, K;
   int num_m_tiles, num_n_tiles;   // in units of the 256 x 256 pair tile
   const float* bias;
+  long long* dbg;   // optional per-CTA cycle counters (vt_debug_set_buffer); null in production
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -125,7 +133,11 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
 }
 
-__device__ __forceinline__ float gelu_epi(float x) { return gelu_erf(x); }
+#ifdef VT_GELU_5TERM
+__device__ __forceinline__ float gelu_epi(float x) { return gelu_erf_fast(x); }
+#else
+__device__ __forceinline__ float gelu_epi(float x) { return gelu_erf_bf16(x); }
+#endif
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -143,23 +155,29 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   auto empty_bar = [&](int s) { return bar_addr + 8u * (kStages + s); };
   auto tfull_bar = [&](int s) { return bar_addr + 8u * (2 * kStages + s); };
   auto tempty_bar = [&](int s) { return bar_addr + 8u * (2 * kStages + 2 + s); };
-  auto res_bar = [&](int w, int c) { return bar_addr + 8u * (2 * kStages + 4 + 2 * w + c); };
+  auto res_bar = [&](int w, int c) { return bar_addr + 8u * (2 * kStages + 4 + kChunks * w + c); };
   const uint32_t tmem_slot = bar_addr + 8u * kNumBars;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
       smem_gen + kStages * kStageBytes + kEpiBytes + 8 * kNumBars);
 
+  // Warp roles.  The warp scheduler favours the highest warp id among eligible warps, so the
+  // single-thread MMA issuer and the TMA producer sit ABOVE the epilogue warps: with the issuer at
+  // warp 1 the GELU epilogue starved it of issue slots (tensor pipe idle 30 % of the fc1 GEMM).
+  constexpr int kWarpTmem = kEpiWarps;          // TMEM alloc / dealloc
+  constexpr int kWarpProducer = kEpiWarps + 2;
+  constexpr int kWarpMma = kEpiWarps + 3;
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
   const bool is_leader = (cta_rank == 0);
 
-  if (warp_idx == 0 && lane == 0) {
+  if (warp_idx == kWarpProducer && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     tma_prefetch_desc(&tma_out);
     if (EPI & EPI_RES) tma_prefetch_desc(&tma_res);
   }
-  if (warp_idx == 1 && lane == 0) {
+  if (warp_idx == kWarpMma && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);      // leader's producer arrive.expect_tx (covers both CTAs' bytes)
       mbar_init(empty_bar(s), 1);     // multicast tcgen05.commit
@@ -168,13 +186,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       mbar_init(tfull_bar(s), 1);                 // multicast tcgen05.commit
       mbar_init(tempty_bar(s), 2 * kEpiWarps);    // epilogue warps of BOTH CTAs (leader's copy is used)
     }
-    for (int w = 0; w < kEpiWarps; ++w) {
-      mbar_init(res_bar(w, 0), 1);
-      mbar_init(res_bar(w, 1), 1);
-    }
+    for (int w = 0; w < kEpiWarps; ++w)
+      for (int c = 0; c < kChunks; ++c) mbar_init(res_bar(w, c), 1);
     fence_barrier_init();
   }
-  if (warp_idx == 2) {
+  if (warp_idx == kWarpTmem) {
     tmem_alloc_2cta<512>(tmem_slot);
     tmem_relinquish_2cta();
   }
@@ -185,68 +201,93 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_kb = (p.K + BK - 1) / BK;
+  long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long dbg_t0 = p.dbg ? clock64() : 0;
   const int first_tile = static_cast<int>(cluster_id_x());
   const int tile_step = static_cast<int>(num_clusters_x());
 
-  if (warp_idx == 0) {
+  if (warp_idx == kWarpProducer) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      int s = 0;
-      uint32_t phase = 0;
-      for (int t = first_tile; t < num_tiles; t += tile_step) {
-        const int m_blk = t / p.num_n_tiles;
-        const int n_blk = t - m_blk * p.num_n_tiles;
-        const int a_row = m_blk * (2 * BM) + static_cast<int>(cta_rank) * BM;
-        const int b_row = n_blk * BN + static_cast<int>(cta_rank) * BNH;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(s), phase ^ 1u);
-          const uint32_t a_dst = tiles_addr + s * kStageBytes;
-          const uint32_t b_dst = a_dst + kABytes;
+    // The loop is executed by the whole warp (warp-uniform control flow keeps addresses and
+    // coordinates in uniform registers); one elected lane issues the TMA instructions.
+    int s = 0;
+    uint32_t phase = 0;
+    for (int t = first_tile; t < num_tiles; t += tile_step) {
+      const int m_blk = t / p.num_n_tiles;
+      const int n_blk = t - m_blk * p.num_n_tiles;
+      const int a_row = m_blk * (2 * BM) + static_cast<int>(cta_rank) * BM;
+      const int b_row = n_blk * BN + static_cast<int>(cta_rank) * BNH;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        long long w0 = 0;
+        if (p.dbg) w0 = clock64();
+        mbar_wait(empty_bar(s), phase ^ 1u);
+        if (p.dbg) dbg_acc[4] += clock64() - w0;
+        const uint32_t a_dst = tiles_addr + s * kStageBytes;
+        const uint32_t b_dst = a_dst + kABytes;
+        if (elect_one_sync()) {
           if (is_leader) mbar_arrive_expect_tx(full_bar(s), 2 * kStageBytes);
           tma_load_2d_2cta(&tma_a, full_bar(s), a_dst, kb * BK, a_row, kEvictNormal);
           tma_load_2d_2cta(&tma_b, full_bar(s), b_dst, kb * BK, b_row, kEvictLast);
-          if (++s == kStages) { s = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++s == kStages) { s = 0; phase ^= 1u; }
       }
     }
-  } else if (warp_idx == 1) {
+  } else if (warp_idx == kWarpMma) {
     // ------------------------------------------------------------------ MMA issuer (leader only)
-    if (is_leader && lane == 0) {
+    // Warp-uniform loop, one elected lane issues.  (Issuing from inside an `if (lane == 0)` region
+    // made the compiler wrap every UTCHMMA in an ELECT / R2UR.BROADCAST loop — ~19 instructions
+    // per MMA — and the GELU epilogue then starved the issuer: tensor pipe 56 % instead of 80 %.)
+    if (is_leader) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
       int s = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
       for (int t = first_tile; t < num_tiles; t += tile_step) {
+        long long w0 = 0;
+        if (p.dbg) w0 = clock64();
         mbar_wait(tempty_bar(as), aphase ^ 1u);
+        if (p.dbg) dbg_acc[3] += clock64() - w0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
+          if (p.dbg) w0 = clock64();
           mbar_wait(full_bar(s), phase);
+          if (p.dbg) dbg_acc[2] += clock64() - w0;
           tc_fence_after();
           const uint32_t a_src = tiles_addr + s * kStageBytes;
           const uint32_t b_src = a_src + kABytes;
+          if (elect_one_sync()) {
+            const uint64_t adesc = make_desc_kmajor_sw128(a_src);
+            const uint64_t bdesc = make_desc_kmajor_sw128(b_src);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_ss_2cta(d_tmem, make_desc_kmajor_sw128(a_src + k * 32),
-                         make_desc_kmajor_sw128(b_src + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advancing K by 16 bf16 = 32 bytes = 2 units of the 16-byte start-address field
+              umma_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_2cta(empty_bar(s));
           }
-          umma_commit_2cta(empty_bar(s));
+          __syncwarp();
           if (++s == kStages) { s = 0; phase ^= 1u; }
         }
-        umma_commit_2cta(tfull_bar(as));
+        if (elect_one_sync()) umma_commit_2cta(tfull_bar(as));
+        __syncwarp();
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
-  } else if (warp_idx >= 4) {
+  } else if (warp_idx < kEpiWarps) {
     // ------------------------------------------------------------------ epilogue (both CTAs)
-    const int ew = warp_idx - 4;
+    const int ew = warp_idx;
     const int q = warp_idx & 3;
-    const int half = ew >> 2;
-    const uint32_t stage_buf[2] = {epi_addr + (2 * ew + 0) * kStagingBytes,
-                                   epi_addr + (2 * ew + 1) * kStagingBytes};
-    uint8_t* stage_gen[2] = {smem_gen + kStages * kStageBytes + (2 * ew + 0) * kStagingBytes,
-                             smem_gen + kStages * kStageBytes + (2 * ew + 1) * kStagingBytes};
+    const int cgrp = ew >> 2;   // column group
+    uint32_t stage_buf[kChunks];
+    uint8_t* stage_gen[kChunks];
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      stage_buf[c] = epi_addr + (kChunks * ew + c) * kStagingBytes;
+      stage_gen[c] = smem_gen + kStages * kStageBytes + (kChunks * ew + c) * kStagingBytes;
+    }
     const int sw = lane & 7;   // swizzle phase of this thread's staging row
     int as = 0;
     uint32_t aphase = 0;
@@ -255,12 +296,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const int m_blk = t / p.num_n_tiles;
       const int n_blk = t - m_blk * p.num_n_tiles;
       const int row0 = m_blk * (2 * BM) + static_cast<int>(cta_rank) * BM + q * 32;
-      const int col0 = n_blk * BN + half * 128;
+      const int col0 = n_blk * BN + cgrp * kColsPerWarp;
 
       if (EPI & EPI_RES) {
         if (lane == 0) {
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < kChunks; ++c) {
             mbar_arrive_expect_tx(res_bar(ew, c), kStagingBytes);
             tma_load_2d(&tma_res, res_bar(ew, c), stage_buf[c], col0 + c * kChunkCols, row0,
                         kEvictFirst);
@@ -268,43 +309,48 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         }
       }
 
+      long long w0 = 0;
+      if (p.dbg) w0 = clock64();
       mbar_wait(tfull_bar(as), aphase);
+      if (p.dbg) { const long long w1 = clock64(); dbg_acc[0] += w1 - w0; w0 = w1; }
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + half * 128;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + cgrp * kColsPerWarp;
 
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32(t_addr + c * kChunkCols, r0);
-        tmem_ld_32x32(t_addr + c * kChunkCols + 32, r1);
-        tmem_ld_wait();
-        if (c == 1) {
-          // accumulator fully read: hand the TMEM stage back to the MMA issuer before the math
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_leader(tempty_bar(as));
-        }
+      for (int c = 0; c < kChunks; ++c) {
         const int col = col0 + c * kChunkCols;
-        if (col < p.N) {   // warp-uniform
-          if (EPI & EPI_RES) mbar_wait(res_bar(ew, c), rphase);
-          uint8_t* rowp = stage_gen[c] + lane * 128;
+        const bool live = col < p.N;   // warp-uniform: chunk not entirely right of the matrix
+        if (EPI & EPI_RES) mbar_wait(res_bar(ew, c), rphase);
+        uint8_t* rowp = stage_gen[c] + lane * 128;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            // 8 consecutive columns: col + 8j .. col + 8j + 7
-            const uint32_t* rr = (j < 4) ? &r0[8 * j] : &r1[8 * (j - 4)];
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_addr + c * kChunkCols + hh * 32, r);
+          // bias for these 32 columns: issued before the TMEM wait so both latencies overlap
+          float4 bv[8];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int cb = col + hh * 32 + 4 * g;
+            bv[g] = (p.bias != nullptr && cb + 3 < p.N)   // N % 8 == 0: groups of 4 are all in or all out
+                        ? __ldg(reinterpret_cast<const float4*>(p.bias + cb))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          tmem_ld_wait();
+          if (c == kChunks - 1 && hh == 1) {
+            // accumulator fully read: hand the TMEM stage back to the MMA issuer before the math
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(tempty_bar(as));
+          }
+          if (!live) continue;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = hh * 4 + jj;           // 16-byte group within the 128-byte staging row
             float v[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(rr[e]);
-            if (p.bias != nullptr) {
-              const int cb = col + 8 * j;
-              float4 b0, b1;
-              if (cb + 7 < p.N) {
-                b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cb));
-                b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + 4));
-              } else {
-                b0 = make_float4(0.f, 0.f, 0.f, 0.f);
-                b1 = b0;   // N is a multiple of 8: a partial group of 8 cannot occur, only a fully OOB one
-              }
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * jj + e]);
+            {
+              const float4 b0 = bv[2 * jj], b1 = bv[2 * jj + 1];
               v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
               v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
             }
@@ -327,32 +373,42 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             o4.w = pack_bf16x2(v[6], v[7]);
             *slot = o4;
           }
+        }
+        if (live) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tma_out, stage_buf[c], col, row0);
             tma_store_commit();
           }
-        } else if (EPI & EPI_RES) {
-          mbar_wait(res_bar(ew, c), rphase);   // keep the barrier phase in step (load was all-OOB)
         }
       }
+      if (p.dbg) { const long long w1 = clock64(); dbg_acc[1] += w1 - w0; w0 = w1; }
       // staging buffers must be drained (read by the TMA engine) before the next tile reuses them
       if (lane == 0) tma_store_wait_read<0>();
       __syncwarp();
+      if (p.dbg) dbg_acc[6] += clock64() - w0;
       rphase ^= 1u;
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
     if (lane == 0) tma_store_wait<0>();
   }
 
+  if (p.dbg && lane == 0 && (warp_idx == kWarpProducer || warp_idx == kWarpMma || warp_idx == 0)) {
+    long long* d = p.dbg + static_cast<long long>(blockIdx.x) * 8;
+    if (warp_idx == 0) { d[0] = dbg_acc[0]; d[1] = dbg_acc[1]; d[6] = dbg_acc[6]; d[5] = clock64() - dbg_t0; }
+    if (warp_idx == kWarpMma) { d[2] = dbg_acc[2]; d[3] = dbg_acc[3]; }
+    if (warp_idx == kWarpProducer) { d[4] = dbg_acc[4]; }
+  }
   tc_fence_before();
   cluster_sync_all();
-  if (warp_idx == 2) {
+  if (warp_idx == kWarpTmem) {
     tc_fence_after();
     tmem_dealloc_2cta<512>(tmem_base);
   }
 }
+
+long long* g_dbg_buffer = nullptr;
 
 int g_num_sms2 = 0;
 int num_sms2() {
@@ -383,6 +439,8 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
 }
 
 }  // namespace
+
+void gemm2_set_debug_buffer(void* ptr) { g_dbg_buffer = static_cast<long long*>(ptr); }
 
 // bf16 in / bf16 out 2-CTA GEMM.  Same argument meaning as gemm_bf16_tcgen05 (out dtype fixed).
 int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long ldb, void* out,
@@ -416,6 +474,7 @@ int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long l
   p.num_m_tiles = (M + 2 * BM - 1) / (2 * BM);
   p.num_n_tiles = (N + BN - 1) / BN;
   p.bias = bias;
+  p.dbg = g_dbg_buffer;
   if (gelu) return launch2<EPI_GELU>(ta, tb, to, tr, p, stream);
   if (residual) return launch2<EPI_RES>(ta, tb, to, tr, p, stream);
   return launch2<0>(ta, tb, to, tr, p, stream);

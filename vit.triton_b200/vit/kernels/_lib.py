@@ -45,6 +45,10 @@ SIGNATURES = {
 
 
 def lib_path() -> str:
+    # VT_LIB selects an alternative build of the same library (A/B measurements of kernel variants)
+    override = os.environ.get("VT_LIB")
+    if override:
+        return override
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 
