@@ -17,10 +17,13 @@ int gemm_bf16_tcgen05(const void*, long long, const void*, long long, void*, lon
 int gemm2_bf16_tcgen05(const void*, long long, const void*, long long, void*, long long, const float*,
                        const void*, long long, int, int, int, int, cudaStream_t);
 void gemm2_set_debug_buffer(void*);
+void attn2_set_debug_buffer(void*);
 int simt_gemm(const void*, const void*, void*, const void*, int, int, int, int, int,
               const long long*, const long long*, const long long*, float, int, int, cudaStream_t);
 int attn_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
                      long long, long long, long long, float, cudaStream_t);
+int attn2_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
+                      long long, long long, long long, float, cudaStream_t);
 int patch_embed_tcgen05(const void*, int, const void*, long long, const float*, void*, int, int,
                         int, int, int, int, cudaStream_t);
 int patching(const void*, void*, int, int, int, int, int, int, cudaStream_t);
@@ -37,6 +40,7 @@ int vt_version(void) { return 100; }
 
 // Developer hook (not part of the public header): per-CTA cycle counters of the 2-CTA GEMM.
 void vt_debug_set_buffer(void* ptr) { vt::gemm2_set_debug_buffer(ptr); }
+void vt_debug_set_attn_buffer(void* ptr) { vt::attn2_set_debug_buffer(ptr); }
 
 const char* vt_status_string(int status) {
   switch (status) {
@@ -98,6 +102,14 @@ int vt_gemm_strided(const void* A, const void* B, void* C, const void* bias, int
 int vt_flash_attn(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H,
                   int32_t N, int32_t dh, int64_t qkv_row_stride, int64_t qkv_batch_stride,
                   int64_t out_row_stride, int64_t out_batch_stride, float scale, void* stream) {
+  // persistent pipelined kernel (attn2_sm100.cu); VT_ATTN_IMPL=1 selects the one-tile-per-CTA kernel
+  static const int impl = [] {
+    const char* e = getenv("VT_ATTN_IMPL");
+    return (e && e[0] == '1') ? 1 : 2;
+  }();
+  if (impl == 2)
+    return vt::attn2_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
+                                 out_row_stride, out_batch_stride, scale, S(stream));
   return vt::attn_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
                               out_row_stride, out_batch_stride, scale, S(stream));
 }

@@ -12,9 +12,12 @@
 // from the NCHW pixels into the SWIZZLE_128B K-major smem layout the UMMA descriptor expects
 // (TMA cannot express a 14-pixel, 28-byte inner box, and C=3 rules out im2col-mode TMA).
 // B (conv weight viewed as [D, 3*P*P], already K-major) arrives by TMA.
-//   warp 0      TMA producer for B + TMEM alloc
-//   warp 1      MMA issuer (M=128, N=256, K=16)
-//   warps 2-5   A gather producers, then epilogue (TMEM -> + posb -> global)
+//   warps 0-7   A gather producers (256 threads, half a tile row each, software-pipelined through a
+//               register ring so several K blocks of pixel loads are in flight), then epilogue
+//   warp 8      TMA producer for B + TMEM alloc
+//   warp 9      MMA issuer (M=128, N=256, K=16), warp-uniform loop with one elected lane
+// Two CTAs are co-resident per SM (2 smem stages each), so one CTA's epilogue overlaps the other's
+// gather / MMA phase.
 #include "common.cuh"
 #include "tensormap.h"
 
@@ -25,8 +28,11 @@ namespace {
 constexpr int PE_BM = 128;
 constexpr int PE_BN = 256;
 constexpr int PE_BK = 64;
-constexpr int PE_STAGES = 4;
-constexpr int PE_THREADS = 192;
+constexpr int PE_STAGES = 2;
+constexpr int PE_GATHER_THREADS = 256;
+constexpr int PE_THREADS = PE_GATHER_THREADS + 64;
+constexpr int PE_WARP_TMA = 8;
+constexpr int PE_WARP_MMA = 9;
 constexpr int PE_A_BYTES = PE_BM * PE_BK * 2;
 constexpr int PE_B_BYTES = PE_BN * PE_BK * 2;
 constexpr int PE_STAGE_BYTES = PE_A_BYTES + PE_B_BYTES;
@@ -47,9 +53,46 @@ struct PatchParams {
 __device__ __forceinline__ float px_to_f(float v) { return v; }
 __device__ __forceinline__ float px_to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
 
+// Raw (unconverted) pixels of one 8-element K chunk, as loaded: converting at load time would make
+// the thread wait for the load and defeat the prefetch ring.
+template <typename TPix, bool kVec>
+struct RawChunk;
+template <>
+struct RawChunk<__nv_bfloat16, true> {
+  uint4 v;
+  __device__ __forceinline__ void zero() { v = make_uint4(0u, 0u, 0u, 0u); }
+  __device__ __forceinline__ void load(const __nv_bfloat16* src) { v = __ldg(reinterpret_cast<const uint4*>(src)); }
+  __device__ __forceinline__ uint4 packed() const { return v; }
+};
+template <>
+struct RawChunk<float, true> {
+  float4 a, b;
+  __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); b = a; }
+  __device__ __forceinline__ void load(const float* src) {
+    a = __ldg(reinterpret_cast<const float4*>(src));
+    b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+  }
+  __device__ __forceinline__ uint4 packed() const {
+    return make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+  }
+};
 template <typename TPix>
-__global__ void __launch_bounds__(PE_THREADS, 1)
+struct RawChunk<TPix, false> {
+  TPix e[8];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = TPix(0.f);
+  }
+  __device__ __forceinline__ uint4 packed() const {
+    return make_uint4(pack_bf16x2(px_to_f(e[0]), px_to_f(e[1])), pack_bf16x2(px_to_f(e[2]), px_to_f(e[3])),
+                      pack_bf16x2(px_to_f(e[4]), px_to_f(e[5])), pack_bf16x2(px_to_f(e[6]), px_to_f(e[7])));
+  }
+};
+
+template <typename TPix, bool kVec>
+__global__ void __launch_bounds__(PE_THREADS, 2)
 patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const PatchParams p) {
+  constexpr int NPF = (kVec && sizeof(TPix) == 2) ? 3 : 2;   // K blocks of pixel loads in flight
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -68,15 +111,15 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const Patc
   const int m_blk = blockIdx.y;
   const int num_kb = (p.K + PE_BK - 1) / PE_BK;
 
-  if (warp_idx == 1 && lane == 0) {
+  if (warp_idx == PE_WARP_MMA && lane == 0) {
     for (int s = 0; s < PE_STAGES; ++s) {
-      mbar_init(full_bar(s), 1 + 128);  // TMA expect_tx arrive + 128 gather threads
+      mbar_init(full_bar(s), 1 + PE_GATHER_THREADS);  // TMA expect_tx arrive + gather threads
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(acc_bar, 1);
     fence_barrier_init();
   }
-  if (warp_idx == 0) {
+  if (warp_idx == PE_WARP_TMA) {
     if (lane == 0) tma_prefetch_desc(&tma_w);
     __syncwarp();
     tmem_alloc<PE_BN>(tmem_slot);
@@ -87,41 +130,43 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const Patc
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  if (warp_idx == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(empty_bar(s), phase ^ 1u);
+  if (warp_idx == PE_WARP_TMA) {
+    int s = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(empty_bar(s), phase ^ 1u);
+      if (elect_one_sync()) {
         const uint32_t b_dst = smem_base + s * PE_STAGE_BYTES + PE_A_BYTES;
         mbar_arrive_expect_tx(full_bar(s), PE_B_BYTES);
         tma_load_2d(&tma_w, full_bar(s), b_dst, kb * PE_BK, n_blk * PE_BN, kEvictLast);
-        if (++s == PE_STAGES) { s = 0; phase ^= 1u; }
       }
+      __syncwarp();
+      if (++s == PE_STAGES) { s = 0; phase ^= 1u; }
     }
-  } else if (warp_idx == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(PE_BM, PE_BN, 0, 0);
-      int s = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full_bar(s), phase);
-        tc_fence_after();
-        const uint32_t a_src = smem_base + s * PE_STAGE_BYTES;
-        const uint32_t b_src = a_src + PE_A_BYTES;
+  } else if (warp_idx == PE_WARP_MMA) {
+    constexpr uint32_t idesc = make_idesc_bf16(PE_BM, PE_BN, 0, 0);
+    int s = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(full_bar(s), phase);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint64_t ad = make_desc_kmajor_sw128(smem_base + s * PE_STAGE_BYTES);
+        const uint64_t bd = make_desc_kmajor_sw128(smem_base + s * PE_STAGE_BYTES + PE_A_BYTES);
 #pragma unroll
-        for (int k = 0; k < PE_BK / 16; ++k) {
-          umma_ss(tmem_base, make_desc_kmajor_sw128(a_src + k * 32),
-                  make_desc_kmajor_sw128(b_src + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < PE_BK / 16; ++k)
+          umma_ss(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
         umma_commit(empty_bar(s));
-        if (++s == PE_STAGES) { s = 0; phase ^= 1u; }
       }
-      umma_commit(acc_bar);
+      __syncwarp();
+      if (++s == PE_STAGES) { s = 0; phase ^= 1u; }
     }
+    if (elect_one_sync()) umma_commit(acc_bar);
+    __syncwarp();
   } else {
-    // ------------------------------------------------------------ gather producers (128 threads)
-    const int r = threadIdx.x - 64;  // tile row owned by this thread, 0..127
+    // ------------------------------------------------------------ gather producers (256 threads)
+    const int r = threadIdx.x & 127;     // tile row
+    const int hh = threadIdx.x >> 7;     // which half of the 64-wide K block: chunks 4*hh .. 4*hh+3
     const long long m = static_cast<long long>(m_blk) * PE_BM + r;
     const bool row_valid = m < static_cast<long long>(p.B) * p.n_patches;
     const int img = row_valid ? static_cast<int>(m / p.n_patches) : 0;
@@ -132,64 +177,66 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const Patc
                            static_cast<long long>(img) * p.C * p.S * p.S +
                            static_cast<long long>(py) * p.P * p.S + px * p.P;
     const int PP = p.P * p.P;
-    const bool vec_ok = (p.P % 8 == 0) && (p.S % 8 == 0);
 
-    int s = 0;
-    uint32_t phase = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      mbar_wait(empty_bar(s), phase ^ 1u);
-      uint8_t* a_row = smem_gen + s * PE_STAGE_BYTES + r * 128;
+    RawChunk<TPix, kVec> ring[NPF][4];
+    auto issue_loads = [&](RawChunk<TPix, kVec> (&dst)[4], int kb) {
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        const int k0 = kb * PE_BK + ch * 8;
-        uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+      for (int ch = 0; ch < 4; ++ch) {
+        const int k0 = kb * PE_BK + (hh * 4 + ch) * 8;
+        dst[ch].zero();
         if (row_valid && k0 < p.K) {
-          if (vec_ok) {
+          if constexpr (kVec) {
             const int c = k0 / PP;
             const int rem = k0 - c * PP;
             const int i = rem / p.P;
             const int j = rem - i * p.P;
-            const TPix* src = img_base + (static_cast<long long>(c) * p.S + i) * p.S + j;
-            if constexpr (sizeof(TPix) == 2) {
-              packed = __ldg(reinterpret_cast<const uint4*>(src));
-            } else {
-              const float4 f0 = __ldg(reinterpret_cast<const float4*>(src));
-              const float4 f1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-              packed.x = pack_bf16x2(f0.x, f0.y);
-              packed.y = pack_bf16x2(f0.z, f0.w);
-              packed.z = pack_bf16x2(f1.x, f1.y);
-              packed.w = pack_bf16x2(f1.z, f1.w);
-            }
+            dst[ch].load(img_base + (static_cast<long long>(c) * p.S + i) * p.S + j);
           } else {
-            float f[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const int k = k0 + e;
-              f[e] = 0.f;
               if (k < p.K) {
                 const int c = k / PP;
                 const int rem = k - c * PP;
                 const int i = rem / p.P;
                 const int j = rem - i * p.P;
-                f[e] = px_to_f(img_base[(static_cast<long long>(c) * p.S + i) * p.S + j]);
+                dst[ch].e[e] = img_base[(static_cast<long long>(c) * p.S + i) * p.S + j];
               }
             }
-            packed.x = pack_bf16x2(f[0], f[1]);
-            packed.y = pack_bf16x2(f[2], f[3]);
-            packed.z = pack_bf16x2(f[4], f[5]);
-            packed.w = pack_bf16x2(f[6], f[7]);
           }
         }
-        *reinterpret_cast<uint4*>(a_row + ((ch ^ (r & 7)) << 4)) = packed;
       }
+    };
+    int s = 0;
+    uint32_t phase = 0;
+    auto publish = [&](const RawChunk<TPix, kVec> (&src)[4]) {
+      mbar_wait(empty_bar(s), phase ^ 1u);
+      uint8_t* a_row = smem_gen + s * PE_STAGE_BYTES + r * 128;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+        *reinterpret_cast<uint4*>(a_row + (((hh * 4 + ch) ^ (r & 7)) << 4)) = src[ch].packed();
       fence_proxy_async_smem();  // make generic-proxy smem writes visible to the tensor core
       mbar_arrive(full_bar(s));
       if (++s == PE_STAGES) { s = 0; phase ^= 1u; }
+    };
+
+#pragma unroll
+    for (int u = 0; u < NPF - 1; ++u)
+      if (u < num_kb) issue_loads(ring[u], u);
+    for (int kb0 = 0; kb0 < num_kb; kb0 += NPF) {
+#pragma unroll
+      for (int u = 0; u < NPF; ++u) {
+        const int kb = kb0 + u;
+        if (kb < num_kb) {
+          if (kb + NPF - 1 < num_kb) issue_loads(ring[(u + NPF - 1) % NPF], kb + NPF - 1);
+          publish(ring[u]);
+        }
+      }
     }
 
-    // ------------------------------------------------------------ epilogue
-    const int quarter = warp_idx & 3;
-    // TMEM lane == tile row; this warp may only read lanes [32*quarter, 32*quarter+32)
+    // ------------------------------------------------------------ epilogue (8 warps)
+    const int quarter = warp_idx & 3;       // TMEM lane quarter this warp may read
+    const int chalf = warp_idx >> 2;        // column half of the tile
     const int er = quarter * 32 + lane;
     const long long em = static_cast<long long>(m_blk) * PE_BM + er;
     const bool e_valid = em < static_cast<long long>(p.B) * p.n_patches;
@@ -202,7 +249,8 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const Patc
     mbar_wait(acc_bar, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < PE_BN; c += 32) {
+    for (int cc = 0; cc < PE_BN / 2; cc += 32) {
+      const int c = chalf * (PE_BN / 2) + cc;
       const int col = n_blk * PE_BN + c;
       uint32_t rr[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c, rr);
@@ -256,7 +304,7 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const Patc
     if (m_blk == 0) {
       const int ncols = min(PE_BN, p.D - n_blk * PE_BN);
       const int total = p.B * ncols;
-      for (int idx = r; idx < total; idx += 128) {
+      for (int idx = threadIdx.x; idx < total; idx += PE_GATHER_THREADS) {
         const int b = idx / ncols;
         const int c = idx - b * ncols;
         const int col = n_blk * PE_BN + c;
@@ -270,11 +318,24 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const Patc
 
   tc_fence_before();
   __syncthreads();
-  if (warp_idx == 0) {
+  if (warp_idx == PE_WARP_TMA) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc<PE_BN>(tmem_base);
   }
+}
+
+template <typename TPix, bool kVec>
+int launch_patch(const CUtensorMap& tw, const PatchParams& p, dim3 grid, cudaStream_t stream) {
+  auto kern = patch_embed_tcgen05_kernel<TPix, kVec>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PE_SMEM);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  kern<<<grid, PE_THREADS, PE_SMEM, stream>>>(tw, p);
+  return static_cast<int>(cudaGetLastError());
 }
 
 }  // namespace
@@ -311,27 +372,13 @@ int patch_embed_tcgen05(const void* pixels, int pix_dtype, const void* w, long l
   const long long M = static_cast<long long>(B) * p.n_patches;
   dim3 grid((D + PE_BN - 1) / PE_BN, static_cast<unsigned>((M + PE_BM - 1) / PE_BM));
   if (grid.y > 65535) return VT_ERR_UNSUPPORTED;
-  static bool attr_f32 = false, attr_bf16 = false;
-  if (pix_dtype == VT_F32) {
-    auto kern = patch_embed_tcgen05_kernel<float>;
-    if (!attr_f32) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PE_SMEM);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      attr_f32 = true;
-    }
-    kern<<<grid, PE_THREADS, PE_SMEM, stream>>>(tw, p);
-  } else if (pix_dtype == VT_BF16) {
-    auto kern = patch_embed_tcgen05_kernel<__nv_bfloat16>;
-    if (!attr_bf16) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PE_SMEM);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      attr_bf16 = true;
-    }
-    kern<<<grid, PE_THREADS, PE_SMEM, stream>>>(tw, p);
-  } else {
-    return VT_ERR_DTYPE;
-  }
-  return static_cast<int>(cudaGetLastError());
+  const bool vec = (P % 8 == 0) && (S % 8 == 0);
+  if (pix_dtype == VT_F32)
+    return vec ? launch_patch<float, true>(tw, p, grid, stream) : launch_patch<float, false>(tw, p, grid, stream);
+  if (pix_dtype == VT_BF16)
+    return vec ? launch_patch<__nv_bfloat16, true>(tw, p, grid, stream)
+               : launch_patch<__nv_bfloat16, false>(tw, p, grid, stream);
+  return VT_ERR_DTYPE;
 }
 
 }  // namespace vt
