@@ -19,4 +19,4 @@ for (B, H, N) in ((256, 12, 197), (128, 12, 577)):
     d = dbg.view(296, 8).double()
     n = d[:, 4].mean()
     print(f"B={B} N={N}: items/slot {n:.1f}; per item cycles: wait-S {d[:,0].mean()/n:.0f}, softmax {d[:,1].mean()/n:.0f}, "
-          f"wait-O {d[:,2].mean()/n:.0f}, epilogue {d[:,3].mean()/n:.0f}, total {d[:,5].mean()/n:.0f} (kernel cycles {d[:,5].mean():.0f})")
+          f"(pass1 {d[:,6].mean()/n:.0f}) wait-O {d[:,2].mean()/n:.0f}, epilogue {d[:,3].mean()/n:.0f}, total {d[:,5].mean()/n:.0f} (kernel cycles {d[:,5].mean():.0f})")

@@ -43,3 +43,24 @@ with torch.no_grad():
     for k, (n, t) in agg.items():
         print(f"  {k:18s} x{n:3d}  {t*1e3:9.1f} us total  {t/n*1e3:8.1f} us each")
     print(f"  sum of kernels {tot:.3f} ms; first..last event {evs[0][2].elapsed_time(evs[-1][2]):.3f} ms")
+
+# CUPTI view (accurate kernel durations and idle gaps)
+try:
+    from torch.profiler import profile, ProfilerActivity
+    with torch.no_grad():
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                m(x)
+            torch.cuda.synchronize()
+    evts = [e for e in prof.events() if e.device_type.name == "CUDA"]
+    evts.sort(key=lambda e: e.time_range.start)
+    agg = collections.OrderedDict()
+    for e in evts:
+        a = agg.setdefault(e.name[:60], [0, 0.0]); a[0] += 1; a[1] += e.time_range.elapsed_us()
+    tot = sum(t for _, t in agg.values())
+    span = evts[-1].time_range.end - evts[0].time_range.start
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"  [cupti] {t/3:9.1f} us/fwd  x{n//3:3d}  {t/n:8.1f} us each  {k}")
+    print(f"  [cupti] kernels {tot/3/1e3:.3f} ms/fwd, span {span/3/1e3:.3f} ms/fwd, idle {(span-tot)/3/1e3:.3f} ms/fwd")
+except Exception as ex:
+    print("profiler failed:", ex)

@@ -49,7 +49,7 @@ struct Attn2Params {
 
 // per-slot barriers
 enum { A_QFULL = 0, A_QEMPTY, A_KFULL, A_KEMPTY, A_VFULL, A_VEMPTY, A_SFULL, A_PFULL, A_OFULL, A_OREAD,
-       A_PER_SLOT };
+       A_TURN, A_PER_SLOT };
 constexpr int A_NBARS = 2 * A_PER_SLOT;
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
@@ -64,34 +64,45 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 // Returns the block's row sum; m_new_out is the running max including this block (log2 domain).
 __device__ __forceinline__ float softmax_block_pipelined(uint32_t t_lane, int nvalid, int nj,
                                                          float scale_log2, float m_run,
-                                                         float& m_new_out) {
+                                                         float& m_new_out, uint32_t turn_wait,
+                                                         uint32_t turn_parity, uint32_t turn_pass,
+                                                         long long* tp = nullptr) {
+  const long long tp0 = tp ? clock64() : 0;
   const int nfull = nvalid & ~31;   // columns covered by fully valid 32-wide chunks
   float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
   uint32_t ra[32], rb[32];
-  if (nfull > 0) {
-    tmem_ld_32x32(t_lane, ra);
-    tmem_ld_wait();
-  }
-  for (int c = 0; c < nfull; c += 64) {
-    if (c + 32 < nfull) tmem_ld_32x32(t_lane + c + 32, rb);
+  auto max_chunk = [&](const uint32_t (&r)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; i += 8) {
-      mx0 = fmax3(mx0, __uint_as_float(ra[i + 0]), __uint_as_float(ra[i + 1]));
-      mx1 = fmax3(mx1, __uint_as_float(ra[i + 2]), __uint_as_float(ra[i + 3]));
-      mx2 = fmax3(mx2, __uint_as_float(ra[i + 4]), __uint_as_float(ra[i + 5]));
-      mx3 = fmax3(mx3, __uint_as_float(ra[i + 6]), __uint_as_float(ra[i + 7]));
+      mx0 = fmax3(mx0, __uint_as_float(r[i + 0]), __uint_as_float(r[i + 1]));
+      mx1 = fmax3(mx1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+      mx2 = fmax3(mx2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
+      mx3 = fmax3(mx3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
     }
-    tmem_ld_wait();
-    if (c + 32 < nfull) {
-      if (c + 64 < nfull) tmem_ld_32x32(t_lane + c + 64, ra);
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        mx0 = fmax3(mx0, __uint_as_float(rb[i + 0]), __uint_as_float(rb[i + 1]));
-        mx1 = fmax3(mx1, __uint_as_float(rb[i + 2]), __uint_as_float(rb[i + 3]));
-        mx2 = fmax3(mx2, __uint_as_float(rb[i + 4]), __uint_as_float(rb[i + 5]));
-        mx3 = fmax3(mx3, __uint_as_float(rb[i + 6]), __uint_as_float(rb[i + 7]));
-      }
+  };
+  {
+    // pass 1 has nothing else live: keep four 32-column loads (128 registers) in flight per wait
+    int c = 0;
+    for (; c + 128 <= nfull; c += 128) {
+      uint32_t rc[32], rd[32];
+      tmem_ld_32x32(t_lane + c, ra);
+      tmem_ld_32x32(t_lane + c + 32, rb);
+      tmem_ld_32x32(t_lane + c + 64, rc);
+      tmem_ld_32x32(t_lane + c + 96, rd);
       tmem_ld_wait();
+      max_chunk(ra); max_chunk(rb); max_chunk(rc); max_chunk(rd);
+    }
+    if (c + 64 <= nfull) {
+      tmem_ld_32x32(t_lane + c, ra);
+      tmem_ld_32x32(t_lane + c + 32, rb);
+      tmem_ld_wait();
+      max_chunk(ra); max_chunk(rb);
+      c += 64;
+    }
+    if (c + 32 <= nfull) {
+      tmem_ld_32x32(t_lane + c, ra);
+      tmem_ld_wait();
+      max_chunk(ra);
     }
   }
   for (int c = nfull; c < nj; c += 16) {
@@ -104,6 +115,10 @@ __device__ __forceinline__ float softmax_block_pipelined(uint32_t t_lane, int nv
   }
   const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2);
   m_new_out = m_new;
+  if (tp) tp[0] += clock64() - tp0;
+  // The exp pass saturates the MUFU pipe: the two slots take turns so that one slot's exp pass runs
+  // while the other does its MUFU-free work (row max, O read, epilogue, MMA waits).
+  if (turn_wait) mbar_wait(turn_wait, turn_parity);
 
   float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
   auto exp_chunk = [&](const uint32_t (&r)[32], int c) {
@@ -128,12 +143,12 @@ __device__ __forceinline__ float softmax_block_pipelined(uint32_t t_lane, int nv
     // P for columns [c, c+32) overwrites S columns [c/2, c/2+16): always left of (or inside) data
     // this thread has already pulled into registers, including the prefetched chunk c+32.
     if (c + 32 < nfull) tmem_ld_32x32(t_lane + c + 32, rb);
-    tmem_ld_wait();
     exp_chunk(ra, c);
+    tmem_ld_wait();
     if (c + 32 < nfull) {
       if (c + 64 < nfull) tmem_ld_32x32(t_lane + c + 64, ra);
-      tmem_ld_wait();
       exp_chunk(rb, c + 32);
+      tmem_ld_wait();
     }
   }
   for (int c = nfull; c < nj; c += 16) {
@@ -153,6 +168,7 @@ __device__ __forceinline__ float softmax_block_pipelined(uint32_t t_lane, int nv
     }
     tmem_st_32x8(t_lane + (c >> 1), pk);
   }
+  if (turn_pass) mbar_arrive(turn_pass);
   tmem_st_wait();
   return (ps0 + ps1) + (ps2 + ps3);
 }
@@ -255,7 +271,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     for (int s = 0; s < 2; ++s) {
       const uint32_t b0 = bar_base + 8u * (s * A_PER_SLOT);
       for (int i = 0; i < A_PER_SLOT; ++i)
-        mbar_init(b0 + 8u * i, (i == A_PFULL || i == A_OREAD) ? 128 : 1);
+        mbar_init(b0 + 8u * i, (i == A_PFULL || i == A_OREAD || i == A_TURN) ? 128 : 1);
     }
     fence_barrier_init();
   }
@@ -323,6 +339,12 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   } else if (is_mma) {
     // ------------------------------------------------------------------ MMA issuer of slot g
     uint32_t step = 0;
+#ifdef VT_ATTN_STAGGER
+    if (g == 1) {   // start slot 1 half a period late so the two slots' softmax phases interleave
+      const long long t0 = clock64();
+      while (clock64() - t0 < VT_ATTN_STAGGER) { }
+    }
+#endif
     for (int it = 0; it < n_local; ++it) {
       for (int j = 0; j < nblk; ++j, ++step) {
         const uint32_t ph = step & 1u;
@@ -368,8 +390,10 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     const uint32_t stage_addr = o_smem + quarter * 4096;
     uint8_t* stage_row = smem_gen + g * slot_bytes + kQBytes + quarter * 4096 + lane * 128;
     const int sw = lane & 7;
+    const uint32_t other_turn = bar_base + 8u * ((1 - g) * A_PER_SLOT + A_TURN);
     uint32_t step = 0;
     long long dacc[4] = {0, 0, 0, 0};
+    long long pass1 = 0;
     const long long dt0 = p.dbg ? clock64() : 0;
 
     for (int it = 0; it < n_local; ++it) {
@@ -390,11 +414,16 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         if (p.dbg) { c1 = clock64(); dacc[0] += c1 - c0; c0 = c1; }
         tc_fence_after();
         float m_new;
-        const float l = softmax_block_pipelined(t_lane, nvalid, nj, p.scale_log2, -INFINITY, m_new);
+        const bool wait_turn = !(g == 0 && it == 0);
+        const uint32_t turn_par = static_cast<uint32_t>(g == 0 ? it - 1 : it) & 1u;
+        const float l = softmax_block_pipelined(t_lane, nvalid, nj, p.scale_log2, -INFINITY, m_new,
+                                                wait_turn ? bar(A_TURN) : 0u, turn_par, other_turn,
+                                                p.dbg ? &pass1 : nullptr);
         tc_fence_before();
         mbar_arrive(bar(A_PFULL));
         if (p.dbg) { c1 = clock64(); dacc[1] += c1 - c0; c0 = c1; }
-        const float inv = 1.0f / l;
+        float inv;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(l));
         mbar_wait(bar(A_OFULL), ph);
         if (p.dbg) { c1 = clock64(); dacc[2] += c1 - c0; c0 = c1; }
         tc_fence_after();
@@ -473,7 +502,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     if (p.dbg && (warp_idx & 3) == 0 && lane == 0) {
       long long* d = p.dbg + (2LL * blockIdx.x + g) * 8;
       d[0] = dacc[0]; d[1] = dacc[1]; d[2] = dacc[2]; d[3] = dacc[3];
-      d[4] = n_local; d[5] = clock64() - dt0;
+      d[4] = n_local; d[5] = clock64() - dt0; d[6] = pass1;
     }
   }
 
