@@ -342,7 +342,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {
-        "kernel": "gemm_bf16_tcgen05_kernel", "bound": "tensor", "achieved": gemm_tflops,
+        "kernel": "gemm2_bf16_kernel (tcgen05 cta_group::2)", "bound": "tensor", "achieved": gemm_tflops,
         "peak": peaks["sustained"], "unit": "TFLOP/s",
         "frac": (gemm_tflops / peaks["sustained"]) if gemm_tflops else None,
         "frac_of_burst_peak": (gemm_tflops / peaks["burst"]) if gemm_tflops else None,

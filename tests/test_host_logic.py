@@ -1,0 +1,118 @@
+"""CPU: host-side logic that needs no GPU — weight packing layouts, shard arithmetic, and the
+data-parallel gather over a 2-process gloo group (the same code path NCCL drives on GPUs)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import hf_oracle
+from vit import packing
+from vit.parallel import DataParallelVIT, all_gather_rows, shard_bounds
+from vit.utils import transfer_pretrained_weights
+from vit.vit import VIT
+
+
+def test_shard_bounds_cover_and_partition():
+    for total in (0, 1, 7, 256, 1024, 2048, 1000):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_bounds(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and b >= a
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(AssertionError):
+        shard_bounds(4, 2, 2)
+
+
+@pytest.mark.parametrize("arch", ["tiny-b", "tiny-h"])
+def test_packed_qkv_layout_matches_hf(arch):
+    """pack_attention rebuilds HF's fused (out, in) Q/K/V matrices from the per-head parameters."""
+    hf = hf_oracle.build_hf(arch, seed=0)
+    model = VIT(**hf_oracle.vit_kwargs(arch))
+    transfer_pretrained_weights(hf, model, verbose=False)
+    hsd = hf.state_dict()
+    for l, block in enumerate(model.encoder.layer):
+        pk = block.attention.packed()
+        pre = f"encoder.layer.{l}.attention.attention."
+        want_w = torch.cat([hsd[pre + f"{p}.weight"] for p in ("query", "key", "value")], dim=0)
+        want_b = torch.cat([hsd[pre + f"{p}.bias"] for p in ("query", "key", "value")], dim=0)
+        assert torch.equal(pk.wqkv, want_w) and torch.equal(pk.bqkv, want_b)
+        assert torch.equal(pk.wo, hsd[f"encoder.layer.{l}.attention.output.dense.weight"])
+        mlp = block.packed()
+        assert torch.equal(mlp.w1, hsd[f"encoder.layer.{l}.intermediate.dense.weight"])
+        assert torch.equal(mlp.w2, hsd[f"encoder.layer.{l}.output.dense.weight"])
+    emb = model.embeddings.packed()
+    K = 3 * model.patch_size ** 2
+    assert emb.ldw % 8 == 0 and emb.ldw >= K
+    assert torch.equal(emb.w[:, :K], hsd["embeddings.patch_embeddings.projection.weight"].reshape(-1, K))
+    assert torch.count_nonzero(emb.w[:, K:]) == 0
+    pos = hsd["embeddings.position_embeddings"][0]
+    assert torch.allclose(emb.posb[0], pos[0] + hsd["embeddings.cls_token"].reshape(-1))
+    assert torch.allclose(emb.posb[1:], pos[1:] + hsd["embeddings.patch_embeddings.projection.bias"])
+
+
+def test_packed_cache_invalidation():
+    model = VIT(**hf_oracle.vit_kwargs("tiny-b"))
+    mha = model.encoder.layer[0].attention
+    first = mha.packed()
+    assert mha.packed() is first                      # cached
+    with torch.no_grad():
+        mha.attention[1].key.weight.add_(1.0)         # in-place update bumps the version counter
+    second = mha.packed()
+    assert second is not first and not torch.equal(second.wqkv, first.wqkv)
+    model.load_state_dict(model.state_dict())         # load_state_dict drops the cache
+    assert mha.packed() is not second
+    model.to(torch.bfloat16)                          # _apply drops it and the dtype follows
+    assert mha.packed().wqkv.dtype == torch.bfloat16 and mha.packed().bqkv.dtype == torch.float32
+
+
+class _FakePooled(torch.nn.Module):
+    """Stands in for VIT on CPU: pooled(x) = per-image mean of the pixels, (B, 3)."""
+
+    def pooled(self, x):
+        return x.mean(dim=(2, 3))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _dp_worker(rank, world, port, total, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        full = torch.randn(total, 3, 4, 4, generator=g)
+        dp = DataParallelVIT(_FakePooled())
+        lo, hi = dp.local_slice(total)
+        got = dp(full[lo:hi], total)
+        torch.save(got, os.path.join(out_dir, f"rank{rank}.pt"))
+        rows = all_gather_rows(torch.full((hi - lo, 2), float(rank)), total)
+        torch.save(rows, os.path.join(out_dir, f"rows{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [8, 7])      # equal shards (single-buffer path) and ragged shards
+def test_data_parallel_gather_gloo_world2(tmp_path, total):
+    world = 2
+    mp.spawn(_dp_worker, args=(world, _free_port(), total, str(tmp_path)), nprocs=world, join=True)
+    g = torch.Generator().manual_seed(0)
+    full = torch.randn(total, 3, 4, 4, generator=g)
+    want = full.mean(dim=(2, 3))
+    for r in range(world):
+        got = torch.load(tmp_path / f"rank{r}.pt")
+        assert torch.equal(got, want), f"rank {r} gathered embeddings differ from the single-process result"
+        rows = torch.load(tmp_path / f"rows{r}.pt")
+        lo0, hi0 = shard_bounds(total, world, 0)
+        assert torch.equal(rows[:hi0], torch.zeros(hi0, 2)) and torch.equal(rows[hi0:], torch.ones(total - hi0, 2))
