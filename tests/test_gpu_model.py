@@ -144,3 +144,26 @@ def test_repack_after_weight_update():
         model.load_state_dict(sd)
         after = model(x)
     assert not torch.equal(before, after)
+
+
+def test_layernorm_folding_matches_unfolded_and_hf():
+    """Folding LayerNorm into the GEMM epilogues changes the launch sequence, not the result: both
+    variants stay within the bf16 tolerance of HF and agree closely with each other."""
+    from vit import vit as vit_mod
+    model, hf = _build("vit-b16-224", torch.bfloat16)
+    x = hf_oracle.make_input("vit-b16-224", 3)
+    want = hf_oracle.hf_forward(hf, x)
+    xd = x.to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        plain = model(xd).float().cpu()
+        vit_mod.set_layernorm_folding(True)
+        try:
+            folded = model(xd).float().cpu()
+            again = model(xd).float().cpu()
+        finally:
+            vit_mod.set_layernorm_folding(False)
+    assert torch.equal(folded, again)         # statistics are exchanged without atomics
+    for got in (folded, plain):
+        assert _cos(got, want) >= 0.999 and (got - want).abs().max().item() <= 0.15
+    assert _cos(folded, plain) >= 0.9995
+    assert (folded - want).abs().max().item() <= 1.5 * (plain - want).abs().max().item() + 0.02

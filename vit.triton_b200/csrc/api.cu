@@ -15,7 +15,8 @@ int pool_cls(const void*, void*, int, int, long long, int, cudaStream_t);
 int gemm_bf16_tcgen05(const void*, long long, const void*, long long, void*, long long, int,
                       const float*, const void*, long long, int, int, int, int, cudaStream_t);
 int gemm2_bf16_tcgen05(const void*, long long, const void*, long long, void*, long long, const float*,
-                       const void*, long long, int, int, int, int, cudaStream_t);
+                       const void*, long long, int, int, int, int, const float*, const float*, int, float,
+                       float*, cudaStream_t);
 void gemm2_set_debug_buffer(void*);
 void attn2_set_debug_buffer(void*);
 int simt_gemm(const void*, const void*, void*, const void*, int, int, int, int, int,
@@ -82,10 +83,18 @@ int vt_gemm_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, void* 
     return (e && e[0] == '1') ? 1 : 2;
   }();
   if (out_dtype == VT_BF16 && impl == 2)
-    return vt::gemm2_bf16_tcgen05(A, lda, Bt, ldb, out, ldo, bias, residual, ldr, M, N, K, gelu,
-                                  S(stream));
+    return vt::gemm2_bf16_tcgen05(A, lda, Bt, ldb, out, ldo, bias, residual, ldr, M, N, K, gelu, nullptr,
+                                  nullptr, 0, 0.f, nullptr, S(stream));
   return vt::gemm_bf16_tcgen05(A, lda, Bt, ldb, out, ldo, out_dtype, bias, residual, ldr, M, N, K,
                                gelu, S(stream));
+}
+
+int vt_gemm_bf16_ln(const void* A, int64_t lda, const void* Bt, int64_t ldb, void* out, int64_t ldo,
+                    const float* bias, const void* residual, int64_t ldr, int32_t M, int32_t N, int32_t K,
+                    int32_t gelu, const float* rowstats, const float* colsum, int32_t ln_dim, float ln_eps,
+                    float* stats_out, void* stream) {
+  return vt::gemm2_bf16_tcgen05(A, lda, Bt, ldb, out, ldo, bias, residual, ldr, M, N, K, gelu, rowstats,
+                                colsum, ln_dim, ln_eps, stats_out, S(stream));
 }
 
 int vt_gemm_strided(const void* A, const void* B, void* C, const void* bias, int32_t M, int32_t N,

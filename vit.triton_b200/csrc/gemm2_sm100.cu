@@ -49,12 +49,21 @@ constexpr int kNumBars = 2 * kStages + 4 + kChunks * kEpiWarps;
 constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiBytes + 8 * kNumBars + 16;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;             // clears the CTA-rank bit of a cluster smem address
 
-enum : int { EPI_GELU = 1, EPI_RES = 2 };
+enum : int { EPI_GELU = 1, EPI_RES = 2, EPI_LNF = 4, EPI_STATS = 8 };
 
 struct Gemm2Params {
   int M, N, K;
   int num_m_tiles, num_n_tiles;   // in units of the 256 x 256 pair tile
   const float* bias;
+  // LayerNorm folded into the epilogue (EPI_LNF): out = rstd_m * acc + (-rstd_m * mean_m) * colsum_n + bias_n
+  // with (sum, sumsq) of the A row given as ln_parts partial pairs rowstats[(m*ln_parts + i)*2 .. +1]
+  const float* rowstats;
+  const float* colsum;
+  float ln_inv_dim, ln_eps;
+  int ln_parts;
+  // EPI_STATS: write (sum, sumsq) of every 64-column chunk of every output row to
+  // stats_out[(m * (N/64) + chunk) * 2 .. +1]: no atomics, so results are bit-reproducible
+  float* stats_out;
   long long* dbg;   // optional per-CTA cycle counters (vt_debug_set_buffer); null in production
 };
 
@@ -309,6 +318,24 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         }
       }
 
+      float ln_a = 1.f, ln_b = 0.f;
+      if (EPI & EPI_LNF) {
+        const int row = row0 + lane;
+        if (row < p.M) {
+          const float2* parts = reinterpret_cast<const float2*>(p.rowstats) + static_cast<long long>(row) * p.ln_parts;
+          float sx = 0.f, sq = 0.f;
+          for (int i = 0; i < p.ln_parts; ++i) {   // fixed order: deterministic
+            const float2 st = __ldg(parts + i);
+            sx += st.x;
+            sq += st.y;
+          }
+          const float mean = sx * p.ln_inv_dim;
+          const float var = fmaxf(sq * p.ln_inv_dim - mean * mean, 0.f);
+          ln_a = rsqrtf(var + p.ln_eps);
+          ln_b = -ln_a * mean;
+        }
+      }
+
       long long w0 = 0;
       if (p.dbg) w0 = clock64();
       mbar_wait(tfull_bar(as), aphase);
@@ -322,6 +349,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         const bool live = col < p.N;   // warp-uniform: chunk not entirely right of the matrix
         if (EPI & EPI_RES) mbar_wait(res_bar(ew, c), rphase);
         uint8_t* rowp = stage_gen[c] + lane * 128;
+        float st_sum = 0.f, st_sq = 0.f;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           uint32_t r[32];
@@ -334,6 +362,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             bv[g] = (p.bias != nullptr && cb + 3 < p.N)   // N % 8 == 0: groups of 4 are all in or all out
                         ? __ldg(reinterpret_cast<const float4*>(p.bias + cb))
                         : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (EPI & EPI_LNF) {
+              if (cb + 3 < p.N) {
+                const float4 cs = __ldg(reinterpret_cast<const float4*>(p.colsum + cb));
+                bv[g].x = fmaf(ln_b, cs.x, bv[g].x);
+                bv[g].y = fmaf(ln_b, cs.y, bv[g].y);
+                bv[g].z = fmaf(ln_b, cs.z, bv[g].z);
+                bv[g].w = fmaf(ln_b, cs.w, bv[g].w);
+              }
+            }
           }
           tmem_ld_wait();
           if (c == kChunks - 1 && hh == 1) {
@@ -351,8 +388,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * jj + e]);
             {
               const float4 b0 = bv[2 * jj], b1 = bv[2 * jj + 1];
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              if (EPI & EPI_LNF) {
+                v[0] = fmaf(v[0], ln_a, b0.x); v[1] = fmaf(v[1], ln_a, b0.y);
+                v[2] = fmaf(v[2], ln_a, b0.z); v[3] = fmaf(v[3], ln_a, b0.w);
+                v[4] = fmaf(v[4], ln_a, b1.x); v[5] = fmaf(v[5], ln_a, b1.y);
+                v[6] = fmaf(v[6], ln_a, b1.z); v[7] = fmaf(v[7], ln_a, b1.w);
+              } else {
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
             }
             uint4* slot = reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4));
             if (EPI & EPI_RES) {
@@ -366,12 +410,27 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = gelu_epi(v[e]);
             }
+            if (EPI & EPI_STATS) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                st_sum += v[e];
+                st_sq = fmaf(v[e], v[e], st_sq);
+              }
+            }
             uint4 o4;
             o4.x = pack_bf16x2(v[0], v[1]);
             o4.y = pack_bf16x2(v[2], v[3]);
             o4.z = pack_bf16x2(v[4], v[5]);
             o4.w = pack_bf16x2(v[6], v[7]);
             *slot = o4;
+          }
+        }
+        if (EPI & EPI_STATS) {
+          const int row = row0 + lane;
+          if (live && row < p.M) {
+            float2* dst = reinterpret_cast<float2*>(p.stats_out) +
+                          static_cast<long long>(row) * (p.N >> 6) + (col >> 6);
+            *dst = make_float2(st_sum, st_sq);
           }
         }
         if (live) {
@@ -442,17 +501,26 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
 
 void gemm2_set_debug_buffer(void* ptr) { g_dbg_buffer = static_cast<long long*>(ptr); }
 
-// bf16 in / bf16 out 2-CTA GEMM.  Same argument meaning as gemm_bf16_tcgen05 (out dtype fixed).
+// bf16 in / bf16 out 2-CTA GEMM.  Same argument meaning as gemm_bf16_tcgen05 (out dtype fixed), plus
+// the optional LayerNorm fold (rowstats + colsum: the A operand is the un-normalised activation and
+// the weights carry gamma) and the optional output row statistics for the next fold.
 int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long ldb, void* out,
                        long long ldo, const float* bias, const void* residual, long long ldr, int M,
-                       int N, int K, int gelu, cudaStream_t stream) {
+                       int N, int K, int gelu, const float* rowstats, const float* colsum, int ln_dim,
+                       float ln_eps, float* stats_out, cudaStream_t stream) {
   if (!A || !Bt || !out || M <= 0 || N <= 0 || K <= 0) return VT_ERR_ARG;
   if (gelu && residual) return VT_ERR_UNSUPPORTED;
+  if ((rowstats != nullptr) != (colsum != nullptr)) return VT_ERR_ARG;
+  if (rowstats && (residual || stats_out || ln_dim <= 0)) return VT_ERR_UNSUPPORTED;
+  if (stats_out && (!residual || (N % 64))) return VT_ERR_UNSUPPORTED;
+  if (rowstats && (ln_dim % 64)) return VT_ERR_UNSUPPORTED;
   if ((K % 8) || (lda % 8) || (ldb % 8) || (N % 8) || (ldo % 8) || (residual && (ldr % 8)))
     return VT_ERR_ALIGN;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bt) |
        reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(residual) |
-       reinterpret_cast<uintptr_t>(bias)) & 15)
+       reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(colsum)) & 15)
+    return VT_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(rowstats) | reinterpret_cast<uintptr_t>(stats_out)) & 7)
     return VT_ERR_ALIGN;
 
   CUtensorMap ta, tb, to, tr;
@@ -474,9 +542,18 @@ int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long l
   p.num_m_tiles = (M + 2 * BM - 1) / (2 * BM);
   p.num_n_tiles = (N + BN - 1) / BN;
   p.bias = bias;
+  p.rowstats = rowstats;
+  p.colsum = colsum;
+  p.ln_inv_dim = ln_dim > 0 ? 1.0f / static_cast<float>(ln_dim) : 0.f;
+  p.ln_eps = ln_eps;
+  p.ln_parts = ln_dim / 64;
+  p.stats_out = stats_out;
   p.dbg = g_dbg_buffer;
+  if (rowstats) return gelu ? launch2<EPI_LNF | EPI_GELU>(ta, tb, to, tr, p, stream)
+                            : launch2<EPI_LNF>(ta, tb, to, tr, p, stream);
   if (gelu) return launch2<EPI_GELU>(ta, tb, to, tr, p, stream);
-  if (residual) return launch2<EPI_RES>(ta, tb, to, tr, p, stream);
+  if (residual) return stats_out ? launch2<EPI_RES | EPI_STATS>(ta, tb, to, tr, p, stream)
+                                 : launch2<EPI_RES>(ta, tb, to, tr, p, stream);
   return launch2<0>(ta, tb, to, tr, p, stream);
 }
 

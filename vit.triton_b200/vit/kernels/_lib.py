@@ -30,6 +30,8 @@ SIGNATURES = {
     "vt_softmax": [_c_ptr, _c_ptr, _c_i64, _c_i32, _c_i64, _c_i32, _c_ptr],
     "vt_gemm_bf16": [_c_ptr, _c_i64, _c_ptr, _c_i64, _c_ptr, _c_i64, _c_i32, _c_ptr, _c_ptr, _c_i64,
                      _c_i32, _c_i32, _c_i32, _c_i32, _c_ptr],
+    "vt_gemm_bf16_ln": [_c_ptr, _c_i64, _c_ptr, _c_i64, _c_ptr, _c_i64, _c_ptr, _c_ptr, _c_i64, _c_i32, _c_i32,
+                        _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i32, _c_f32, _c_ptr, _c_ptr],
     "vt_gemm_strided": [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32,
                         _c_i64p, _c_i64p, _c_i64p, _c_f32, _c_i32, _c_i32, _c_ptr],
     "vt_flash_attn": [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i64, _c_i64,

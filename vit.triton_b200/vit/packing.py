@@ -17,28 +17,34 @@ from .kernels import _lib
 
 
 class PackedMixin:
-    """Gives a module a lazily built, automatically invalidated ``packed()`` namespace."""
+    """Gives a module lazily built, automatically invalidated ``packed(kind)`` namespaces.
+
+    ``kind`` selects a builder ``_build_packed[_<kind>]`` and its source list
+    ``_packed_sources[_<kind>]`` (default: every parameter of the module)."""
 
     def _packed_sources(self):
         return list(self.parameters())
 
-    def _packed_key(self, params):
+    @staticmethod
+    def _packed_key(params):
         return tuple((p.data_ptr(), p._version) for p in params)
 
-    def packed(self):
-        state = self.__dict__.get("_packed_state")
+    def packed(self, kind: str = ""):
+        states = self.__dict__.setdefault("_packed_states", {})
+        state = states.get(kind)
         if state is not None:
             params, key, value = state
             if self._packed_key(params) == key:
                 return value
-        params = self._packed_sources()
+        suffix = f"_{kind}" if kind else ""
+        params = getattr(self, "_packed_sources" + suffix, self._packed_sources)()
         with torch.no_grad():
-            value = self._build_packed()
-        self.__dict__["_packed_state"] = (params, self._packed_key(params), value)
+            value = getattr(self, "_build_packed" + suffix)()
+        states[kind] = (params, self._packed_key(params), value)
         return value
 
     def invalidate_packed(self):
-        self.__dict__.pop("_packed_state", None)
+        self.__dict__.pop("_packed_states", None)
 
     def _apply(self, fn, *args, **kwargs):
         self.invalidate_packed()
@@ -79,6 +85,26 @@ def pack_mlp(block) -> SimpleNamespace:
     )
 
 
+def _fold_layernorm(w_nk: torch.Tensor, bias32: torch.Tensor, ln) -> tuple:
+    """Fold y = LN(x) into the dense layer that consumes it:  LN(x) @ W^T + b
+         = rstd * (x @ (W * gamma)^T) - rstd * mean * colsum(W * gamma) + (b + W @ beta).
+    Returns (W * gamma in the weight dtype, b + W @ beta in fp32, row sums of the ROUNDED folded weight)."""
+    w32 = w_nk.float()
+    w_fold = (w32 * ln.weight.detach().float()[None, :]).to(w_nk.dtype).contiguous()
+    b_fold = (bias32 + w32 @ ln.bias.detach().float()).contiguous()
+    colsum = w_fold.float().sum(dim=1).contiguous()
+    return w_fold, b_fold, colsum
+
+
+def pack_block_folded(block) -> SimpleNamespace:
+    """layernorm_before folded into the QKV weights of one encoder block.  (layernorm_after -> fc1 is
+    NOT folded: the extra per-element FMAs land in the GELU epilogue, which already paces that GEMM —
+    measured +35 us per layer against the 31 us LayerNorm kernel it would remove.)"""
+    att = block.attention.packed()
+    wqkv, bqkv, cqkv = _fold_layernorm(att.wqkv, att.bqkv, block.layernorm_before)
+    return SimpleNamespace(wqkv=wqkv, bqkv=bqkv, cqkv=cqkv)
+
+
 def pack_embeddings(emb) -> SimpleNamespace:
     w = emb.projection.weight.detach()
     D = w.shape[0]
@@ -92,6 +118,38 @@ def pack_embeddings(emb) -> SimpleNamespace:
     posb[1:] += emb.projection.bias.detach().float()
     return SimpleNamespace(w=w2d, ldw=kpad, K=K, posb=posb.contiguous(),
                            bias32=emb.projection.bias.detach().float().contiguous())
+
+
+def folding_supported(x: torch.Tensor, dim: int, mlp_dim: int) -> bool:
+    """LayerNorm folding runs on the bf16 tensor-core GEMM only."""
+    return x.is_cuda and x.dtype == torch.bfloat16 and dim % 64 == 0 and mlp_dim % 8 == 0
+
+
+def linear_ln(x: torch.Tensor, w_fold: torch.Tensor, b_fold: torch.Tensor, colsum: torch.Tensor,
+              rowstats: torch.Tensor, eps: float, gelu: bool = False) -> torch.Tensor:
+    """out = act(LN(x) @ W^T + b) computed as a GEMM on the un-normalised x with the normalisation
+    applied per row in the epilogue; ``rowstats`` is the (M, K/64, 2) fp32 table of per-64-column
+    (sum, sumsq) partials of x's rows written by ``linear_res_stats``."""
+    B, N, K = x.shape
+    n_out = w_fold.shape[0]
+    out = torch.empty((B, N, n_out), device=x.device, dtype=x.dtype)
+    _lib.call("vt_gemm_bf16_ln", x.data_ptr(), K, w_fold.data_ptr(), K, out.data_ptr(), n_out,
+              b_fold.data_ptr(), None, 0, B * N, n_out, K, 1 if gelu else 0, rowstats.data_ptr(),
+              colsum.data_ptr(), K, float(eps), None, _lib.stream_ptr(x))
+    return out
+
+
+def linear_res_stats(x: torch.Tensor, w_nk: torch.Tensor, bias32: torch.Tensor, residual: torch.Tensor,
+                     stats_out: torch.Tensor) -> torch.Tensor:
+    """out = x @ W^T + b + residual, also writing every output row's per-64-column (sum, sumsq) partials
+    into the (M, N/64, 2) fp32 ``stats_out`` for the LayerNorm folded into the next GEMM."""
+    B, N, K = x.shape
+    n_out = w_nk.shape[0]
+    out = torch.empty((B, N, n_out), device=x.device, dtype=x.dtype)
+    _lib.call("vt_gemm_bf16_ln", x.data_ptr(), K, w_nk.data_ptr(), K, out.data_ptr(), n_out,
+              bias32.data_ptr(), residual.data_ptr(), n_out, B * N, n_out, K, 0, None, None, 0, 0.0,
+              stats_out.data_ptr(), _lib.stream_ptr(x))
+    return out
 
 
 def linear(x: torch.Tensor, w_nk: torch.Tensor, bias32: torch.Tensor, gelu: bool = False,

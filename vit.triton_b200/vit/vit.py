@@ -37,6 +37,10 @@ from .kernels import _lib
 from .kernels.layernorm import layernorm
 
 _FUSED = True
+# Folding layernorm_before into the QKV GEMM epilogue is implemented and tested but OFF by default:
+# measured at C2 it removes a 31.5 us LayerNorm launch per block and adds ~14 us to the QKV GEMM and
+# ~10 us to the fc2 GEMM (statistics output), a net gain inside run-to-run noise (profiles/README.md).
+_FOLD_LN = False
 
 
 def set_fused(enabled: bool) -> None:
@@ -48,6 +52,13 @@ def set_fused(enabled: bool) -> None:
 
 def fused_enabled() -> bool:
     return _FUSED
+
+
+def set_layernorm_folding(enabled: bool) -> None:
+    """Toggle folding of layernorm_before into the QKV GEMM epilogue (default on; only affects the
+    fused bf16 path; default OFF, see the note at _FOLD_LN).  Off = 7 launches per block."""
+    global _FOLD_LN
+    _FOLD_LN = bool(enabled)
 
 
 class LinearWithBias(nn.Module):
@@ -151,6 +162,33 @@ class Transformer(packing.PackedMixin, nn.Module):
     def _build_packed(self):
         return packing.pack_mlp(self)
 
+    def _packed_sources_folded(self):
+        return list(self.parameters())
+
+    def _build_packed_folded(self):
+        return packing.pack_block_folded(self)
+
+    def forward_folded(self, x: torch.Tensor, ln1_stats: Optional[torch.Tensor]):
+        """Block forward with layernorm_before folded into the QKV GEMM (bf16 only).
+
+        ``ln1_stats``: (M, D/64, 2) fp32 per-64-column (sum, sumsq) partials of x's rows, written by the
+        previous block's last GEMM (None for the first block: layernorm_before then runs as a
+        kernel).  Returns (output, statistics of the output rows).  6 launches instead of 7."""
+        att = self.attention.packed()
+        mlp = self.packed()
+        x = x.contiguous()
+        if ln1_stats is None:
+            qkv = packing.linear(self.layernorm_before(x), att.wqkv, att.bqkv)
+        else:
+            pk = self.packed("folded")
+            qkv = packing.linear_ln(x, pk.wqkv, pk.bqkv, pk.cqkv, ln1_stats, self.layernorm_before.eps)
+        ctx = flash_attention(qkv, self.num_heads, 1.0 / math.sqrt(self.d_out))
+        res = packing.linear(ctx, att.wo, att.bo, residual=x)
+        mid = packing.linear(self.layernorm_after(res), mlp.w1, mlp.b1, gelu=True)
+        stats = torch.empty((x.shape[0] * x.shape[1], self.d_in // 64, 2), device=x.device, dtype=torch.float32)
+        out = packing.linear_res_stats(mid, mlp.w2, mlp.b2, res, stats)
+        return out, stats
+
 
 class Encoder(nn.Module):
     """Stack of blocks (reference vit.py:152-170)."""
@@ -168,6 +206,14 @@ class Encoder(nn.Module):
         )
 
     def forward(self, x) -> torch.Tensor:
+        if _FUSED and _FOLD_LN and len(self.layer) > 0 and x.numel() > 0 and \
+                packing.folding_supported(x, self.hidden_dim, self.layer[0].mlp_dim):
+            # layernorm_before of blocks 1.. folded into their QKV GEMM; row statistics of each block's
+            # output are produced by its last GEMM's epilogue
+            ln1_stats = None
+            for layer in self.layer:
+                x, ln1_stats = layer.forward_folded(x, ln1_stats)
+            return x
         for layer in self.layer:
             x = layer(x)
         return x
