@@ -17,6 +17,8 @@ for (B, H, N) in ((256, 12, 197), (128, 12, 577)):
     torch.cuda.synchronize()
     lib.vt_debug_set_attn_buffer(None)
     d = dbg.view(296, 8).double()
-    n = d[:, 4].mean()
-    print(f"B={B} N={N}: items/slot {n:.1f}; per item cycles: wait-S {d[:,0].mean()/n:.0f}, softmax {d[:,1].mean()/n:.0f}, "
-          f"(pass1 {d[:,6].mean()/n:.0f}) wait-O {d[:,2].mean()/n:.0f}, epilogue {d[:,3].mean()/n:.0f}, total {d[:,5].mean()/n:.0f} (kernel cycles {d[:,5].mean():.0f})")
+    nq = (N + 127) // 128
+    n = B * H * nq / 296
+    names = ["wait-S", "pass1", "max-sync", "pass2", "wait-O", "O-read", "epilogue"]
+    print(f"B={B} N={N}: items/slot {n:.1f}; per item cycles: " + ", ".join(f"{nm} {d[:,i].mean()/n:.0f}" for i, nm in enumerate(names))
+          + f", total {d[:,7].mean()/n:.0f}")

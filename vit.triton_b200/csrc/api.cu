@@ -8,7 +8,7 @@
 
 namespace vt {
 int layernorm_rows(const void*, const void*, const void*, void*, long long, int, long long,
-                   long long, float, int, int, cudaStream_t);
+                   long long, float, int, int, int, cudaStream_t);
 int add_elementwise(const void*, const void*, void*, long long, int, cudaStream_t);
 int softmax_rows(const void*, void*, long long, int, long long, int, cudaStream_t);
 int pool_cls(const void*, void*, int, int, long long, int, cudaStream_t);
@@ -16,15 +16,18 @@ int gemm_bf16_tcgen05(const void*, long long, const void*, long long, void*, lon
                       const float*, const void*, long long, int, int, int, int, cudaStream_t);
 int gemm2_bf16_tcgen05(const void*, long long, const void*, long long, void*, long long, const float*,
                        const void*, long long, int, int, int, int, const float*, const float*, int, float,
-                       float*, cudaStream_t);
+                       float*, int, cudaStream_t);
 void gemm2_set_debug_buffer(void*);
 void attn2_set_debug_buffer(void*);
+void attn3_set_debug_buffer(void*);
 int simt_gemm(const void*, const void*, void*, const void*, int, int, int, int, int,
               const long long*, const long long*, const long long*, float, int, int, cudaStream_t);
 int attn_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
                      long long, long long, long long, float, cudaStream_t);
 int attn2_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
-                      long long, long long, long long, float, cudaStream_t);
+                      long long, long long, long long, float, int, cudaStream_t);
+int attn3_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
+                      long long, long long, long long, float, int, cudaStream_t);
 int patch_embed_tcgen05(const void*, int, const void*, long long, const float*, void*, int, int,
                         int, int, int, int, cudaStream_t);
 int patching(const void*, void*, int, int, int, int, int, int, cudaStream_t);
@@ -35,13 +38,30 @@ int conv2d_nchw(const void*, const void*, const void*, void*, int, int, int, int
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
+// Traversal direction of the hot-path kernels.  In the forward every kernel consumes what the
+// previous launch produced; both walk their rows in index order, so by the time the consumer
+// starts, the producer's FIRST rows have long been evicted from L2 while its LAST rows are still
+// resident.  Consecutive launches therefore alternate direction (row tiles / work items from the
+// end): the consumer starts on the rows the producer wrote last.  Results do not depend on the
+// direction; VT_TRAVERSAL=0 disables the alternation (A/B measurements).
+static int next_direction() {
+  static const bool enabled = [] {
+    const char* e = getenv("VT_TRAVERSAL");
+    return !(e && e[0] == '0');
+  }();
+  static thread_local int parity = 0;
+  const int d = parity;
+  parity ^= 1;
+  return enabled ? d : 0;
+}
+
 extern "C" {
 
 int vt_version(void) { return 100; }
 
 // Developer hook (not part of the public header): per-CTA cycle counters of the 2-CTA GEMM.
 void vt_debug_set_buffer(void* ptr) { vt::gemm2_set_debug_buffer(ptr); }
-void vt_debug_set_attn_buffer(void* ptr) { vt::attn2_set_debug_buffer(ptr); }
+void vt_debug_set_attn_buffer(void* ptr) { vt::attn2_set_debug_buffer(ptr); vt::attn3_set_debug_buffer(ptr); }
 
 const char* vt_status_string(int status) {
   switch (status) {
@@ -61,7 +81,7 @@ int vt_layernorm(const void* x, const void* gamma, const void* beta, void* out, 
                  int32_t dim, int64_t in_row_stride, int64_t out_row_stride, float eps,
                  int32_t in_dtype, int32_t out_dtype, void* stream) {
   return vt::layernorm_rows(x, gamma, beta, out, rows, dim, in_row_stride, out_row_stride, eps,
-                            in_dtype, out_dtype, S(stream));
+                            in_dtype, out_dtype, next_direction(), S(stream));
 }
 
 int vt_add(const void* a, const void* b, void* out, int64_t n, int32_t dtype, void* stream) {
@@ -84,7 +104,7 @@ int vt_gemm_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, void* 
   }();
   if (out_dtype == VT_BF16 && impl == 2)
     return vt::gemm2_bf16_tcgen05(A, lda, Bt, ldb, out, ldo, bias, residual, ldr, M, N, K, gelu, nullptr,
-                                  nullptr, 0, 0.f, nullptr, S(stream));
+                                  nullptr, 0, 0.f, nullptr, next_direction(), S(stream));
   return vt::gemm_bf16_tcgen05(A, lda, Bt, ldb, out, ldo, out_dtype, bias, residual, ldr, M, N, K,
                                gelu, S(stream));
 }
@@ -94,7 +114,7 @@ int vt_gemm_bf16_ln(const void* A, int64_t lda, const void* Bt, int64_t ldb, voi
                     int32_t gelu, const float* rowstats, const float* colsum, int32_t ln_dim, float ln_eps,
                     float* stats_out, void* stream) {
   return vt::gemm2_bf16_tcgen05(A, lda, Bt, ldb, out, ldo, bias, residual, ldr, M, N, K, gelu, rowstats,
-                                colsum, ln_dim, ln_eps, stats_out, S(stream));
+                                colsum, ln_dim, ln_eps, stats_out, next_direction(), S(stream));
 }
 
 int vt_gemm_strided(const void* A, const void* B, void* C, const void* bias, int32_t M, int32_t N,
@@ -111,14 +131,18 @@ int vt_gemm_strided(const void* A, const void* B, void* C, const void* bias, int
 int vt_flash_attn(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H,
                   int32_t N, int32_t dh, int64_t qkv_row_stride, int64_t qkv_batch_stride,
                   int64_t out_row_stride, int64_t out_batch_stride, float scale, void* stream) {
-  // persistent pipelined kernel (attn2_sm100.cu); VT_ATTN_IMPL=1 selects the one-tile-per-CTA kernel
+  // persistent kernels: attn3 (two column halves per row, default) / attn2 (VT_ATTN_IMPL=2);
+  // VT_ATTN_IMPL=1 selects the one-tile-per-CTA kernel.  The alternatives exist for A/B measurements.
   static const int impl = [] {
     const char* e = getenv("VT_ATTN_IMPL");
-    return (e && e[0] == '1') ? 1 : 2;
+    return (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 3;
   }();
+  if (impl == 3)
+    return vt::attn3_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
+                                 out_row_stride, out_batch_stride, scale, next_direction(), S(stream));
   if (impl == 2)
     return vt::attn2_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
-                                 out_row_stride, out_batch_stride, scale, S(stream));
+                                 out_row_stride, out_batch_stride, scale, next_direction(), S(stream));
   return vt::attn_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
                               out_row_stride, out_batch_stride, scale, S(stream));
 }

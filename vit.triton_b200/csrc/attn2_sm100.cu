@@ -43,6 +43,7 @@ struct Attn2Params {
   int nqt;            // query tiles per (image, head)
   int bkv, nblk;      // rows per KV block (multiple of 16, <= 256), number of KV blocks
   long long total_items;
+  int reverse;        // walk the items from the last to the first (L2 reuse, see api.cu)
   float scale_log2;
   long long* dbg;   // optional cycle counters (developer builds)
 };
@@ -119,6 +120,7 @@ __device__ __forceinline__ float softmax_block_pipelined(uint32_t t_lane, int nv
   // The exp pass saturates the MUFU pipe: the two slots take turns so that one slot's exp pass runs
   // while the other does its MUFU-free work (row max, O read, epilogue, MMA waits).
   if (turn_wait) mbar_wait(turn_wait, turn_parity);
+  const long long tp1 = tp ? clock64() : 0;
 
   float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
   auto exp_chunk = [&](const uint32_t (&r)[32], int c) {
@@ -170,6 +172,7 @@ __device__ __forceinline__ float softmax_block_pipelined(uint32_t t_lane, int nv
   }
   if (turn_pass) mbar_arrive(turn_pass);
   tmem_st_wait();
+  if (tp) tp[1] += clock64() - tp1;
   return (ps0 + ps1) + (ps2 + ps3);
 }
 
@@ -301,7 +304,8 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   const int bkv = p.bkv;
 
   auto decode = [&](int local, int& img, int& head, int& qt) {
-    const long long item = first_item + static_cast<long long>(local) * item_step;
+    long long item = first_item + static_cast<long long>(local) * item_step;
+    if (p.reverse) item = p.total_items - 1 - item;
     qt = static_cast<int>(item % p.nqt);
     const long long bh = item / p.nqt;
     head = static_cast<int>(bh % p.H);
@@ -393,7 +397,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     const uint32_t other_turn = bar_base + 8u * ((1 - g) * A_PER_SLOT + A_TURN);
     uint32_t step = 0;
     long long dacc[4] = {0, 0, 0, 0};
-    long long pass1 = 0;
+    long long pass1[2] = {0, 0};
     const long long dt0 = p.dbg ? clock64() : 0;
 
     for (int it = 0; it < n_local; ++it) {
@@ -418,7 +422,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         const uint32_t turn_par = static_cast<uint32_t>(g == 0 ? it - 1 : it) & 1u;
         const float l = softmax_block_pipelined(t_lane, nvalid, nj, p.scale_log2, -INFINITY, m_new,
                                                 wait_turn ? bar(A_TURN) : 0u, turn_par, other_turn,
-                                                p.dbg ? &pass1 : nullptr);
+                                                p.dbg ? pass1 : nullptr);
         tc_fence_before();
         mbar_arrive(bar(A_PFULL));
         if (p.dbg) { c1 = clock64(); dacc[1] += c1 - c0; c0 = c1; }
@@ -502,7 +506,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     if (p.dbg && (warp_idx & 3) == 0 && lane == 0) {
       long long* d = p.dbg + (2LL * blockIdx.x + g) * 8;
       d[0] = dacc[0]; d[1] = dacc[1]; d[2] = dacc[2]; d[3] = dacc[3];
-      d[4] = n_local; d[5] = clock64() - dt0; d[6] = pass1;
+      d[4] = n_local; d[5] = clock64() - dt0; d[6] = pass1[0]; d[7] = pass1[1];
     }
   }
 
@@ -522,7 +526,7 @@ void attn2_set_debug_buffer(void* ptr) { g_attn_dbg = static_cast<long long*>(pt
 
 int attn2_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, int B, int H, int N,
                       int dh, long long qkv_row_stride, long long qkv_batch_stride,
-                      long long out_row_stride, long long out_batch_stride, float scale,
+                      long long out_row_stride, long long out_batch_stride, float scale, int reverse,
                       cudaStream_t stream) {
   if (!q || !k || !v || !out || B <= 0 || H <= 0 || N <= 0) return VT_ERR_ARG;
   if (dh != kDH) return VT_ERR_UNSUPPORTED;
@@ -541,6 +545,7 @@ int attn2_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, in
   p.bkv = (bkv + 15) & ~15;
   p.total_items = static_cast<long long>(B) * H * p.nqt;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.reverse = reverse;
   p.dbg = g_attn_dbg;
   const int kv_bytes = p.bkv * kDH * 2;
   const int smem = 1024 + 2 * (kQBytes + kOutBytes + 2 * kv_bytes) + 8 * A_NBARS + 16;

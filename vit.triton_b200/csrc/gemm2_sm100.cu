@@ -54,6 +54,7 @@ enum : int { EPI_GELU = 1, EPI_RES = 2, EPI_LNF = 4, EPI_STATS = 8 };
 struct Gemm2Params {
   int M, N, K;
   int num_m_tiles, num_n_tiles;   // in units of the 256 x 256 pair tile
+  int reverse;                    // walk the row tiles from the last to the first (L2 reuse, see api.cu)
   const float* bias;
   // LayerNorm folded into the epilogue (EPI_LNF): out = rstd_m * acc + (-rstd_m * mean_m) * colsum_n + bias_n
   // with (sum, sumsq) of the A row given as ln_parts partial pairs rowstats[(m*ln_parts + i)*2 .. +1]
@@ -222,8 +223,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     int s = 0;
     uint32_t phase = 0;
     for (int t = first_tile; t < num_tiles; t += tile_step) {
-      const int m_blk = t / p.num_n_tiles;
+      int m_blk = t / p.num_n_tiles;
       const int n_blk = t - m_blk * p.num_n_tiles;
+      if (p.reverse) m_blk = p.num_m_tiles - 1 - m_blk;
       const int a_row = m_blk * (2 * BM) + static_cast<int>(cta_rank) * BM;
       const int b_row = n_blk * BN + static_cast<int>(cta_rank) * BNH;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -302,8 +304,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     uint32_t aphase = 0;
     uint32_t rphase = 0;
     for (int t = first_tile; t < num_tiles; t += tile_step) {
-      const int m_blk = t / p.num_n_tiles;
+      int m_blk = t / p.num_n_tiles;
       const int n_blk = t - m_blk * p.num_n_tiles;
+      if (p.reverse) m_blk = p.num_m_tiles - 1 - m_blk;
       const int row0 = m_blk * (2 * BM) + static_cast<int>(cta_rank) * BM + q * 32;
       const int col0 = n_blk * BN + cgrp * kColsPerWarp;
 
@@ -507,7 +510,7 @@ void gemm2_set_debug_buffer(void* ptr) { g_dbg_buffer = static_cast<long long*>(
 int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long ldb, void* out,
                        long long ldo, const float* bias, const void* residual, long long ldr, int M,
                        int N, int K, int gelu, const float* rowstats, const float* colsum, int ln_dim,
-                       float ln_eps, float* stats_out, cudaStream_t stream) {
+                       float ln_eps, float* stats_out, int reverse, cudaStream_t stream) {
   if (!A || !Bt || !out || M <= 0 || N <= 0 || K <= 0) return VT_ERR_ARG;
   if (gelu && residual) return VT_ERR_UNSUPPORTED;
   if ((rowstats != nullptr) != (colsum != nullptr)) return VT_ERR_ARG;
@@ -541,6 +544,7 @@ int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long l
   p.M = M; p.N = N; p.K = K;
   p.num_m_tiles = (M + 2 * BM - 1) / (2 * BM);
   p.num_n_tiles = (N + BN - 1) / BN;
+  p.reverse = reverse;
   p.bias = bias;
   p.rowstats = rowstats;
   p.colsum = colsum;

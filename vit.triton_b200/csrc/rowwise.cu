@@ -63,11 +63,12 @@ template <typename T, typename TO, int VPL>
 __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
                       const T* __restrict__ beta, TO* __restrict__ out, long long rows, int dim,
-                      long long in_stride, long long out_stride, float eps) {
+                      long long in_stride, long long out_stride, float eps, int reverse) {
   constexpr int EV = Vec<T>::N;
   const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
+  if (reverse) row = rows - 1 - row;   // blocks are scheduled in index order: last rows first
   const T* xr = x + row * in_stride;
   const int nvec = dim / EV;
 
@@ -151,7 +152,7 @@ layernorm_generic_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
 
 template <typename T, typename TO>
 int launch_layernorm(const void* x, const void* g, const void* b, void* out, long long rows,
-                     int dim, long long in_stride, long long out_stride, float eps,
+                     int dim, long long in_stride, long long out_stride, float eps, int reverse,
                      cudaStream_t stream) {
   constexpr int EV = Vec<T>::N;
   const int warps = 8;
@@ -168,7 +169,8 @@ int launch_layernorm(const void* x, const void* g, const void* b, void* out, lon
 #define VT_LN_CASE(V)                                                                        \
   case V:                                                                                    \
     layernorm_rows_kernel<T, TO, V><<<grid, warps * 32, 0, stream>>>(xp, gp, bp, op, rows, dim, \
-                                                                     in_stride, out_stride, eps); \
+                                                                     in_stride, out_stride, eps, \
+                                                                     reverse);                   \
     break;
   switch (vpl) {
     VT_LN_CASE(1) VT_LN_CASE(2) VT_LN_CASE(3) VT_LN_CASE(4) VT_LN_CASE(5) VT_LN_CASE(6)
@@ -288,18 +290,18 @@ __global__ void pool_cls_kernel(const T* __restrict__ x, T* __restrict__ out, in
 
 int layernorm_rows(const void* x, const void* gamma, const void* beta, void* out, long long rows,
                    int dim, long long in_stride, long long out_stride, float eps, int in_dtype,
-                   int out_dtype, cudaStream_t stream) {
+                   int out_dtype, int reverse, cudaStream_t stream) {
   if (!x || !gamma || !beta || !out || rows < 0 || dim <= 0) return VT_ERR_ARG;
   if (rows == 0) return VT_OK;
   if (in_dtype == VT_F32 && out_dtype == VT_F32)
     return launch_layernorm<float, float>(x, gamma, beta, out, rows, dim, in_stride, out_stride,
-                                          eps, stream);
+                                          eps, reverse, stream);
   if (in_dtype == VT_BF16 && out_dtype == VT_BF16)
     return launch_layernorm<__nv_bfloat16, __nv_bfloat16>(x, gamma, beta, out, rows, dim,
-                                                          in_stride, out_stride, eps, stream);
+                                                          in_stride, out_stride, eps, reverse, stream);
   if (in_dtype == VT_F32 && out_dtype == VT_BF16)
     return launch_layernorm<float, __nv_bfloat16>(x, gamma, beta, out, rows, dim, in_stride,
-                                                  out_stride, eps, stream);
+                                                  out_stride, eps, reverse, stream);
   return VT_ERR_DTYPE;
 }
 
