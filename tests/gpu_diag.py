@@ -151,6 +151,17 @@ def fam_attn():
         torch.cuda.synchronize()
         want = _attn_ref(qkv, H)
         print(f"attn B={B} H={H} N={N}: rel err {rel(got, want):.3e} max {(got.float()-want).abs().max().item():.3e} finite {bool(torch.isfinite(got.float()).all())}")
+    for (B, H, N) in ((1, 1, 16), (1, 2, 64), (1, 1, 128), (2, 16, 257), (1, 3, 500)):
+        qkv = torch.randn(B, N, 3 * H * 80, device="cuda").bfloat16()
+        got = flash_attention(qkv, H)
+        torch.cuda.synchronize()
+        want = _attn_ref(qkv, H)
+        print(f"attn dh80 B={B} H={H} N={N}: rel err {rel(got, want):.3e} max {(got.float()-want).abs().max().item():.3e} finite {bool(torch.isfinite(got.float()).all())}")
+        if rel(got, want) > 2e-2:
+            e = (got.float() - want).abs()[0]
+            hd = e.view(N, H, 80)
+            print("   err by head-dim column block (16 wide):", [round(hd[:, :, i:i+16].max().item(), 3) for i in range(0, 80, 16)])
+            print("   err by row block (32):", [round(e[i:i+32].max().item(), 3) for i in range(0, min(N, 256), 32)])
     for (B, H, N) in ((256, 12, 197), (128, 12, 577)):
         qkv = torch.randn(B, N, 3 * H * 64, device="cuda").bfloat16()
         for _ in range(3):

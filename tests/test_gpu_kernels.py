@@ -210,6 +210,18 @@ def test_flash_attention_bf16(B, H, N):
     assert rel_err(got, want) <= 1e-2
 
 
+@pytest.mark.parametrize("B,H,N", [(2, 16, 257), (1, 2, 17), (1, 1, 128), (1, 3, 500), (1, 1, 1), (2, 2, 208), (1, 2, 209)])
+def test_flash_attention_bf16_head_dim_80(B, H, N):
+    """ViT-H heads (dh = 80): 64-column SWIZZLE_128B + 16-column SWIZZLE_32B operand tiles."""
+    from vit.kernels import flash_attention
+    qkv = torch.randn(B, N, 3 * H * 80, device=dev()).bfloat16()
+    got = flash_attention(qkv, H)
+    want = _attn_ref(qkv, H)
+    assert got.shape == (B, N, H * 80) and torch.isfinite(got.float()).all()
+    assert (got.float() - want).abs().max().item() <= 2e-2, f"max err {(got.float() - want).abs().max().item()}"
+    assert rel_err(got, want) <= 1e-2
+
+
 def test_flash_attention_peaky_scores():
     """Large logits: the online max subtraction must keep exp() in range."""
     from vit.kernels import flash_attention

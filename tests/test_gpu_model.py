@@ -167,3 +167,17 @@ def test_layernorm_folding_matches_unfolded_and_hf():
         assert _cos(got, want) >= 0.999 and (got - want).abs().max().item() <= 0.15
     assert _cos(folded, plain) >= 0.9995
     assert (folded - want).abs().max().item() <= 1.5 * (plain - want).abs().max().item() + 0.02
+
+
+@pytest.mark.parametrize("arch", ["vit-l16-224", "vit-h14-224"])
+def test_c4_c5_architectures_bf16_match_hf(arch):
+    """BASELINE configs 3 / 4 (ViT-L/16, ViT-H/14: 14-pixel patches, K = 588, dh = 80, 257 tokens) at
+    full width and depth on the two images the CPU oracle finishes in seconds."""
+    model, hf = _build(arch, torch.bfloat16)
+    x = hf_oracle.make_input(arch, 2)
+    want = hf_oracle.hf_forward(hf, x)
+    with torch.no_grad():
+        got = model(x.to(DEV, torch.bfloat16)).float().cpu()
+    assert torch.isfinite(got).all()
+    assert _cos(got, want) >= 0.999, f"cosine {_cos(got, want)}"
+    assert (got - want).abs().max().item() <= 0.2, f"max-abs {(got - want).abs().max().item()}"

@@ -1,6 +1,6 @@
 // K3 (main variant): persistent fused attention forward on tcgen05, two slots x two column halves.
 //
-//   ctx[b, i, h*64:(h+1)*64] = softmax_j( scale * q[b,i,h] . k[b,j,h] ) @ v[b,j,h]      (bf16, dh = 64)
+//   ctx[b, i, h*dh:(h+1)*dh] = softmax_j( scale * q[b,i,h] . k[b,j,h] ) @ v[b,j,h]   (bf16, dh = 64 | 80)
 //
 // Replaces the reference's per-head matmul3 -> softmax -> matmul3 -> slice-assign chain
 // (vit/vit.py:60-72,101-108) for all heads at once; the score matrix never leaves the SM.
@@ -26,6 +26,10 @@
 //                             ([128, 192) for short blocks, where P1 would overlap [0, 64))
 // Row max and row sum are exchanged between the two halves through shared memory (one named
 // barrier each); everything else is as in attn2.
+//
+// Head dim 80 (ViT-H): 160-byte rows do not fit the 128-byte swizzle, so every Q/K/V tile is loaded
+// as a 64-column SWIZZLE_128B part plus a 16-column SWIZZLE_32B part; QK^T gets a fifth K step on
+// the 32-byte tiles and P.V a second MMA (N = 16) per K step into output columns [64, 80).
 #include "common.cuh"
 #include "tensormap.h"
 
@@ -33,12 +37,11 @@ namespace vt {
 
 namespace {
 
-constexpr int kDH = 64;
+constexpr int kDM = 64;                               // columns of the SWIZZLE_128B part of a head
 constexpr int kQTile = 128;
 constexpr int kSoftmaxWarps = 16;
 constexpr int kThreads3 = (kSoftmaxWarps + 4) * 32;   // 640
-constexpr int kQBytes = kQTile * kDH * 2;             // 16 KB
-constexpr int kOutBytes = kQTile * kDH * 2;           // 16 KB staging per slot: 8 warps x [32 rows x 64 B]
+constexpr int kQMainBytes = kQTile * kDM * 2;         // 16 KB
 constexpr int kSlotCols = 256;
 constexpr int kP0Col = 208;
 constexpr int kMaxBkv = 208;
@@ -75,9 +78,9 @@ __device__ __forceinline__ int col_split(int nj) {
   return cs;
 }
 
-// O_j must not overlap P1 = [cs, cs + (nj-cs)/2): columns [0, 64) when the split leaves them free,
-// else (short blocks, nj < 128) columns [128, 192)
-__device__ __forceinline__ int out_col(int cs) { return cs >= 64 ? 0 : 128; }
+// O_j (dh columns) must not overlap P1 = [cs, cs + (nj-cs)/2): columns [128, 128+dh) when P1 ends at or
+// before 128, else columns [0, dh) (then cs = 96 >= dh)
+__device__ __forceinline__ int out_col(int cs, int nj) { return (cs + ((nj - cs) >> 1) <= 128) ? 128 : 0; }
 
 // Row max over this thread's score columns [c0, c1) of which [c0, min(c1, nvalid_end)) are valid.
 __device__ __forceinline__ float row_max_part(uint32_t t_lane, int c0, int c1, int nvalid) {
@@ -161,17 +164,30 @@ __device__ __forceinline__ float exp_part(uint32_t t_lane, int c0, int c1, int n
   return (ps0 + ps1) + (ps2 + ps3);
 }
 
+// shared-memory bytes of one slot: [Q main][K main][V main][Q tail][K tail][V tail][O staging]
+__host__ __device__ constexpr int slot_bytes_for(int dh, int bkv) {
+  return kQTile * dh * 2 + 2 * bkv * dh * 2 + 8 * 32 * (dh / 2) * 2;
+}
+
+template <int DH>
 __global__ void __launch_bounds__(kThreads3, 1)
 attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                  const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_o,
-                 const Attn3Params p) {
+                 const __grid_constant__ CUtensorMap tma_qt, const __grid_constant__ CUtensorMap tma_kt,
+                 const __grid_constant__ CUtensorMap tma_vt, const Attn3Params p) {
+  constexpr int kDH = DH;
+  constexpr int kDT = DH - kDM;                            // 0 or 16: columns of the SWIZZLE_32B part
+  constexpr int kHalfCols = DH / 2;                        // output columns per softmax thread
+  constexpr int kStageTile = 32 * kHalfCols * 2;           // staging bytes per warp
+  static_assert(DH == 64 || DH == 80, "head dim 64 or 80");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  const int kv_bytes = p.bkv * kDH * 2;                  // one K or V block
-  const int slot_bytes = kQBytes + kOutBytes + 2 * kv_bytes;
-  // slot layout: [Q 16 KB][O staging 16 KB][K][V]; then barriers, TMEM slot, row-statistics exchange
+  const int kv_main = p.bkv * kDM * 2;                   // SWIZZLE_128B part of one K or V block
+  const int kv_tail = p.bkv * kDT * 2;                   // SWIZZLE_32B part
+  const int slot_bytes = slot_bytes_for(DH, p.bkv);
+  // then barriers, TMEM slot, row-statistics exchange
   const uint32_t bar_base = smem_base + 2 * slot_bytes;
   const uint32_t tmem_slot = bar_base + 8u * A_NBARS;
   const int misc_off = 2 * slot_bytes + 8 * A_NBARS;
@@ -189,9 +205,13 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
 
   const uint32_t slot_smem = smem_base + g * slot_bytes;
   const uint32_t q_smem = slot_smem;
-  const uint32_t o_smem = slot_smem + kQBytes;
-  const uint32_t k_smem = o_smem + kOutBytes;
-  const uint32_t v_smem = k_smem + kv_bytes;
+  const uint32_t k_smem = q_smem + kQMainBytes;
+  const uint32_t v_smem = k_smem + kv_main;
+  const uint32_t qt_smem = v_smem + kv_main;
+  const uint32_t kt_smem = qt_smem + kQTile * kDT * 2;
+  const uint32_t vt_smem = kt_smem + kv_tail;
+  const uint32_t o_smem = vt_smem + kv_tail;
+  const int o_off = g * slot_bytes + kQMainBytes + 2 * kv_main + kQTile * kDT * 2 + 2 * kv_tail;
   auto bar = [&](int i) { return bar_base + 8u * (g * A_PER_SLOT + i); };
 
   if (warp_idx == 19 && lane == 0) {
@@ -207,6 +227,11 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     tma_prefetch_desc(&tma_k);
     tma_prefetch_desc(&tma_v);
     tma_prefetch_desc(&tma_o);
+    if (kDT) {
+      tma_prefetch_desc(&tma_qt);
+      tma_prefetch_desc(&tma_kt);
+      tma_prefetch_desc(&tma_vt);
+    }
   }
   if (warp_idx == 16) {
     tmem_alloc<512>(tmem_slot);
@@ -245,22 +270,25 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       decode(it, img, head, qt);
       mbar_wait(bar(A_QEMPTY), (static_cast<uint32_t>(it) & 1u) ^ 1u);
       if (elect_one_sync()) {
-        mbar_arrive_expect_tx(bar(A_QFULL), kQBytes);
+        mbar_arrive_expect_tx(bar(A_QFULL), kQTile * kDH * 2);
         tma_load_3d(&tma_q, bar(A_QFULL), q_smem, head * kDH, qt * kQTile, img, kEvictFirst);
+        if (kDT) tma_load_3d(&tma_qt, bar(A_QFULL), qt_smem, head * kDH + kDM, qt * kQTile, img, kEvictFirst);
       }
       __syncwarp();
       for (int j = 0; j < nblk; ++j, ++step) {
         const uint32_t ph = step & 1u;
         mbar_wait(bar(A_KEMPTY), ph ^ 1u);
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(bar(A_KFULL), kv_bytes);
+          mbar_arrive_expect_tx(bar(A_KFULL), kv_main + kv_tail);
           tma_load_3d(&tma_k, bar(A_KFULL), k_smem, head * kDH, j * bkv, img, kEvictNormal);
+          if (kDT) tma_load_3d(&tma_kt, bar(A_KFULL), kt_smem, head * kDH + kDM, j * bkv, img, kEvictNormal);
         }
         __syncwarp();
         mbar_wait(bar(A_VEMPTY), ph ^ 1u);
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(bar(A_VFULL), kv_bytes);
+          mbar_arrive_expect_tx(bar(A_VFULL), kv_main + kv_tail);
           tma_load_3d(&tma_v, bar(A_VFULL), v_smem, head * kDH, j * bkv, img, kEvictNormal);
+          if (kDT) tma_load_3d(&tma_vt, bar(A_VFULL), vt_smem, head * kDH + kDM, j * bkv, img, kEvictNormal);
         }
         __syncwarp();
       }
@@ -285,7 +313,9 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
           const uint64_t qd = make_desc_kmajor_sw128(q_smem);
           const uint64_t kd = make_desc_kmajor_sw128(k_smem);
 #pragma unroll
-          for (int k = 0; k < kDH / 16; ++k) umma_ss(t_slot, qd + 2 * k, kd + 2 * k, idesc, k != 0 ? 1u : 0u);
+          for (int k = 0; k < kDM / 16; ++k) umma_ss(t_slot, qd + 2 * k, kd + 2 * k, idesc, k != 0 ? 1u : 0u);
+          if (kDT)   // fifth K step on the 16-column SWIZZLE_32B tiles (rows of 32 B, 8-row atoms of 256 B)
+            umma_ss(t_slot, make_smem_desc(qt_smem, 0, 256, 6), make_smem_desc(kt_smem, 0, 256, 6), idesc, 1u);
           umma_commit(bar(A_SFULL));
           umma_commit(bar(A_KEMPTY));
           if (j == nblk - 1) umma_commit(bar(A_QEMPTY));
@@ -296,13 +326,17 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         mbar_wait(bar(A_VFULL), ph);
         tc_fence_after();
         if (elect_one_sync()) {
-          const uint32_t idesc = make_idesc_bf16(kQTile, kDH, 0, 1);
+          const uint32_t idesc = make_idesc_bf16(kQTile, kDM, 0, 1);
+          const uint32_t idesc_t = make_idesc_bf16(kQTile, 16, 0, 1);
           const uint64_t vd = make_desc_mnmajor_sw128(v_smem, 1024);
+          const uint64_t vtd = make_smem_desc(vt_smem, 256, 256, 6);   // MN-major, SWIZZLE_32B
           const int ksteps = nj >> 4;
           const int k0 = cs >> 4;
-          for (int k = 0; k < ksteps; ++k) {   // 16 kv rows = 2048 bytes = 128 units of the address field
+          const uint32_t o_tmem = t_slot + out_col(cs, nj);
+          for (int k = 0; k < ksteps; ++k) {   // 16 kv rows: 2048 B of the main tile, 512 B of the tail tile
             const uint32_t a_tmem = (k < k0) ? (t_slot + kP0Col + 8 * k) : (t_slot + cs + 8 * (k - k0));
-            umma_ts(t_slot + out_col(cs), a_tmem, vd + 128 * k, idesc, k != 0 ? 1u : 0u);
+            umma_ts(o_tmem, a_tmem, vd + 128 * k, idesc, k != 0 ? 1u : 0u);
+            if (kDT) umma_ts(o_tmem + kDM, a_tmem, vtd + 32 * k, idesc_t, k != 0 ? 1u : 0u);
           }
           umma_commit(bar(A_OFULL));
           umma_commit(bar(A_VEMPTY));
@@ -317,9 +351,10 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t t_lane = t_slot + (static_cast<uint32_t>(quarter * 32) << 16);
     const int wslot = (warp_idx & 7);                       // staging tile of this warp within the slot
-    const uint32_t stage_addr = o_smem + wslot * 2048;      // [32 rows x 64 B], SWIZZLE_64B
-    uint8_t* stage_row = smem_gen + g * slot_bytes + kQBytes + wslot * 2048 + lane * 64;
-    const int sw = (lane >> 1) & 3;
+    // [32 rows x 64 B] SWIZZLE_64B (dh 64) or [32 rows x 80 B] unswizzled (dh 80)
+    const uint32_t stage_addr = o_smem + wslot * kStageTile;
+    uint8_t* stage_row = smem_gen + o_off + wslot * kStageTile + lane * (kHalfCols * 2);
+    const int sw = (kDT == 0) ? ((lane >> 1) & 3) : 0;
     float* my_x = xchg + (g * 2 + half) * kQTile + row_in_tile;
     const float* other_x = xchg + (g * 2 + (half ^ 1)) * kQTile + row_in_tile;
     float* my_l = xchg_sum + (g * 2 + half) * kQTile + row_in_tile;
@@ -336,7 +371,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       int img, head, qt;
       decode(it, img, head, qt);
 
-      float o_acc[kDH / 2];
+      float o_acc[kHalfCols];
       float m_run = -INFINITY;
       float l_run = 0.f;      // this thread's partial row sum (its columns only)
 
@@ -385,14 +420,25 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         tc_fence_after();
         {
           uint32_t r[32];
-          tmem_ld_32x32(t_lane + out_col(cs) + half * 32, r);
+          uint32_t r8[8];
+          const uint32_t o_src = t_lane + out_col(cs, nj) + half * kHalfCols;
+          tmem_ld_32x32(o_src, r);
+          if (kDT) tmem_ld_32x8(o_src + 32, r8);
           tmem_ld_wait();
           if (j == 0) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) o_acc[i] = __uint_as_float(r[i]);
+            if (kDT) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o_acc[32 + i] = __uint_as_float(r8[i]);
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) o_acc[i] = fmaf(o_acc[i], alpha, __uint_as_float(r[i]));
+            if (kDT) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o_acc[32 + i] = fmaf(o_acc[32 + i], alpha, __uint_as_float(r8[i]));
+            }
           }
         }
         tc_fence_before();
@@ -410,7 +456,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       if (lane == 0) tma_store_wait_read<0>();   // previous store out of this staging tile is done
       __syncwarp();
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
+      for (int jj = 0; jj < kHalfCols / 8; ++jj) {
         uint4 o4;
         o4.x = pack_bf16x2(o_acc[8 * jj + 0] * inv, o_acc[8 * jj + 1] * inv);
         o4.y = pack_bf16x2(o_acc[8 * jj + 2] * inv, o_acc[8 * jj + 3] * inv);
@@ -425,7 +471,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                      :
                      : "l"(reinterpret_cast<uint64_t>(&tma_o)), "r"(stage_addr),
-                       "r"(head * kDH + half * 32), "r"(row0), "r"(img)
+                       "r"(head * kDH + half * kHalfCols), "r"(row0), "r"(img)
                      : "memory");
         tma_store_commit();
       }
@@ -449,6 +495,25 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
 
 long long* g_attn3_dbg = nullptr;
 
+template <int DH>
+int launch_attn3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+                 const CUtensorMap& tqt, const CUtensorMap& tkt, const CUtensorMap& tvt, const Attn3Params& p,
+                 int smem, cudaStream_t stream) {
+  auto kern = attn3_fwd_kernel<DH>;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    smem_set = smem;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long grid = (p.total_items + 1) / 2 < sms ? (p.total_items + 1) / 2 : sms;
+  kern<<<static_cast<unsigned>(grid), kThreads3, smem, stream>>>(tq, tk, tv, to, tqt, tkt, tvt, p);
+  return static_cast<int>(cudaGetLastError());
+}
+
 }  // namespace
 
 void attn3_set_debug_buffer(void* ptr) { g_attn3_dbg = static_cast<long long*>(ptr); }
@@ -458,7 +523,7 @@ int attn3_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, in
                       long long out_row_stride, long long out_batch_stride, float scale, int reverse,
                       cudaStream_t stream) {
   if (!q || !k || !v || !out || B <= 0 || H <= 0 || N <= 0) return VT_ERR_ARG;
-  if (dh != kDH) return VT_ERR_UNSUPPORTED;
+  if (dh != 64 && dh != 80) return VT_ERR_UNSUPPORTED;
   if ((qkv_row_stride % 8) || (qkv_batch_stride % 8) || (out_row_stride % 8) || (out_batch_stride % 8))
     return VT_ERR_ALIGN;
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
@@ -477,36 +542,32 @@ int attn3_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, in
   p.scale_log2 = scale * 1.4426950408889634f;
   p.reverse = reverse;
   p.dbg = g_attn3_dbg;
-  const int kv_bytes = p.bkv * kDH * 2;
-  const int smem = 1024 + 2 * (kQBytes + kOutBytes + 2 * kv_bytes) + 8 * A_NBARS + 16 + 2 * (2 * 2 * kQTile * 4);
+  const int smem = 1024 + 2 * slot_bytes_for(dh, p.bkv) + 8 * A_NBARS + 16 + 2 * (2 * 2 * kQTile * 4);
   if (smem > kSmemLimit) return VT_ERR_UNSUPPORTED;
 
-  CUtensorMap tq, tk, tv, to;
-  int rc = make_tmap_bf16_3d(&tq, q, static_cast<uint64_t>(H) * dh, N, B, qkv_row_stride, qkv_batch_stride,
-                             dh, kQTile, TMAP_SW_128);
+  const uint64_t cols = static_cast<uint64_t>(H) * dh;
+  CUtensorMap tq, tk, tv, to, tqt, tkt, tvt;
+  int rc = make_tmap_bf16_3d(&tq, q, cols, N, B, qkv_row_stride, qkv_batch_stride, kDM, kQTile, TMAP_SW_128);
   if (rc) return rc;
-  rc = make_tmap_bf16_3d(&tk, k, static_cast<uint64_t>(H) * dh, N, B, qkv_row_stride, qkv_batch_stride, dh,
-                         p.bkv, TMAP_SW_128);
+  rc = make_tmap_bf16_3d(&tk, k, cols, N, B, qkv_row_stride, qkv_batch_stride, kDM, p.bkv, TMAP_SW_128);
   if (rc) return rc;
-  rc = make_tmap_bf16_3d(&tv, v, static_cast<uint64_t>(H) * dh, N, B, qkv_row_stride, qkv_batch_stride, dh,
-                         p.bkv, TMAP_SW_128);
+  rc = make_tmap_bf16_3d(&tv, v, cols, N, B, qkv_row_stride, qkv_batch_stride, kDM, p.bkv, TMAP_SW_128);
   if (rc) return rc;
-  rc = make_tmap_bf16_3d(&to, out, static_cast<uint64_t>(H) * dh, N, B, out_row_stride, out_batch_stride, 32,
-                         32, TMAP_SW_64);
-  if (rc) return rc;
-
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    smem_set = smem;
+  if (dh == 64) {
+    rc = make_tmap_bf16_3d(&to, out, cols, N, B, out_row_stride, out_batch_stride, 32, 32, TMAP_SW_64);
+    if (rc) return rc;
+    tqt = tq; tkt = tk; tvt = tv;   // unused
+    return launch_attn3<64>(tq, tk, tv, to, tqt, tkt, tvt, p, smem, stream);
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  long long grid = (p.total_items + 1) / 2 < sms ? (p.total_items + 1) / 2 : sms;
-  attn3_fwd_kernel<<<static_cast<unsigned>(grid), kThreads3, smem, stream>>>(tq, tk, tv, to, p);
-  return static_cast<int>(cudaGetLastError());
+  rc = make_tmap_bf16_3d(&tqt, q, cols, N, B, qkv_row_stride, qkv_batch_stride, 16, kQTile, TMAP_SW_32);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tkt, k, cols, N, B, qkv_row_stride, qkv_batch_stride, 16, p.bkv, TMAP_SW_32);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tvt, v, cols, N, B, qkv_row_stride, qkv_batch_stride, 16, p.bkv, TMAP_SW_32);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&to, out, cols, N, B, out_row_stride, out_batch_stride, 40, 32, TMAP_SW_NONE);
+  if (rc) return rc;
+  return launch_attn3<80>(tq, tk, tv, to, tqt, tkt, tvt, p, smem, stream);
 }
 
 }  // namespace vt

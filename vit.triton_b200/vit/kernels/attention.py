@@ -31,7 +31,7 @@ def flash_attention(qkv: torch.Tensor, num_heads: int, scale: Optional[float] = 
     base = qkv.data_ptr()
     stream = _lib.stream_ptr(qkv)
 
-    if qkv.dtype == torch.bfloat16 and dh == 64 and qkv.stride(1) % 8 == 0 and qkv.stride(0) % 8 == 0 \
+    if qkv.dtype == torch.bfloat16 and dh in (64, 80) and qkv.stride(1) % 8 == 0 and qkv.stride(0) % 8 == 0 \
             and base % 16 == 0:
         for b0 in range(0, B, 32768):
             nb = min(32768, B - b0)
