@@ -1,4 +1,5 @@
-"""In-kernel cycle accounting of the persistent attention kernel (developer tool)."""
+"""Attention kernel: isolated timing + in-kernel cycle accounting per slot (developer tool).
+VT_LIB=<alternative .so> selects a kernel variant build."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "vit.triton_b200"))
@@ -7,18 +8,30 @@ from vit.kernels import _lib, flash_attention
 lib = _lib.load()
 lib.vt_debug_set_attn_buffer.argtypes = [ctypes.c_void_p]
 lib.vt_debug_set_attn_buffer.restype = None
-for (B, H, N) in ((256, 12, 197), (128, 12, 577)):
-    qkv = torch.randn(B, N, 3 * H * 64, device="cuda").bfloat16()
+shapes = ((256, 12, 197, 64), (128, 12, 577, 64))
+if len(sys.argv) > 1 and sys.argv[1] == "all":
+    shapes += ((128, 16, 197, 64), (64, 16, 257, 80))
+for (B, H, N, dh) in shapes:
+    qkv = torch.randn(B, N, 3 * H * dh, device="cuda").bfloat16()
     for _ in range(3):
         flash_attention(qkv, H)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(20):
+        flash_attention(qkv, H)
+    e.record()
+    torch.cuda.synchronize()
+    us = s.elapsed_time(e) / 20 * 1e3
     dbg = torch.zeros(2 * 148 * 8, dtype=torch.int64, device="cuda")
     lib.vt_debug_set_attn_buffer(dbg.data_ptr())
     flash_attention(qkv, H)
     torch.cuda.synchronize()
     lib.vt_debug_set_attn_buffer(None)
-    d = dbg.view(296, 8).double()
+    d = dbg.view(148, 2, 8).double()
     nq = (N + 127) // 128
     n = B * H * nq / 296
     names = ["wait-S", "pass1", "max-sync", "pass2", "wait-O", "O-read", "epilogue"]
-    print(f"B={B} N={N}: items/slot {n:.1f}; per item cycles: " + ", ".join(f"{nm} {d[:,i].mean()/n:.0f}" for i, nm in enumerate(names))
-          + f", total {d[:,7].mean()/n:.0f}")
+    print(f"B={B} H={H} N={N} dh={dh}: {us:.1f} us/launch (20 back-to-back); items/slot {n:.1f}")
+    for g in range(2):
+        print(f"   slot {g} per item cycles: " + ", ".join(f"{nm} {d[:, g, i].mean()/n:.0f}" for i, nm in enumerate(names))
+              + f", total {d[:, g, 7].mean()/n:.0f}")

@@ -54,11 +54,13 @@ struct Attn3Params {
   long long total_items;
   int reverse;        // walk the items from the last to the first (L2 reuse, see api.cu)
   float scale_log2;
+  __nv_bfloat16* out;                          // direct-store epilogue (VT_A3_DIRECT_STORE)
+  long long out_row_stride, out_batch_stride;  // in elements
   long long* dbg;     // optional cycle counters (developer tool tools/attn_dbg.py)
 };
 
-enum { A_QFULL = 0, A_QEMPTY, A_KFULL, A_KEMPTY, A_VFULL, A_VEMPTY, A_SFULL, A_PFULL, A_OFULL, A_OREAD,
-       A_TURN, A_PER_SLOT };
+enum { A_QFULL = 0, A_QEMPTY, A_KFULL, A_KEMPTY, A_VFULL, A_VEMPTY, A_SFULL, A_PFULL, A_PFULL1, A_OFULL,
+       A_OREAD, A_TURN, A_PER_SLOT };   // A_PFULL / A_PFULL1: probabilities of column half 0 / 1 are in TMEM
 constexpr int A_NBARS = 2 * A_PER_SLOT;
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
@@ -121,6 +123,11 @@ __device__ __forceinline__ float row_max_part(uint32_t t_lane, int c0, int c1, i
 
 // p = exp2(s * scale - m) over this thread's columns [c0, c1); P (bf16x2) written to TMEM columns
 // p_col + (c - c0)/2; returns the partial row sum.  Next chunk's load is in flight during the math.
+#ifdef VT_A3_EXP_NOMUFU   // timing experiment: no MUFU in the exp pass (results wrong)
+#define VT_EX2(x) ((x) * 0.5f)
+#else
+#define VT_EX2(x) ex2_approx(x)
+#endif
 __device__ __forceinline__ float exp_part(uint32_t t_lane, int c0, int c1, int nvalid, uint32_t p_col,
                                           float scale_log2, float m) {
   float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
@@ -133,15 +140,19 @@ __device__ __forceinline__ float exp_part(uint32_t t_lane, int c0, int c1, int n
     uint32_t pk[16];
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float p0 = ex2_approx(fmaf(__uint_as_float(r[i + 0]), scale_log2, -m));
-      const float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m));
-      const float p2 = ex2_approx(fmaf(__uint_as_float(r[i + 2]), scale_log2, -m));
-      const float p3 = ex2_approx(fmaf(__uint_as_float(r[i + 3]), scale_log2, -m));
+      const float p0 = VT_EX2(fmaf(__uint_as_float(r[i + 0]), scale_log2, -m));
+      const float p1 = VT_EX2(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m));
+      const float p2 = VT_EX2(fmaf(__uint_as_float(r[i + 2]), scale_log2, -m));
+      const float p3 = VT_EX2(fmaf(__uint_as_float(r[i + 3]), scale_log2, -m));
       ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
       pk[(i >> 1) + 0] = pack_bf16x2(p0, p1);
       pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
     }
+#ifndef VT_A3_EXP_NOST
     tmem_st_32x16(p_col + ((c - c0) >> 1), pk);
+#else
+    if (pk[3] == 0x12345u) tmem_st_32x16(p_col + ((c - c0) >> 1), pk);
+#endif
   }
   for (; c < c1; c += 16) {
     uint32_t r[16];
@@ -150,8 +161,8 @@ __device__ __forceinline__ float exp_part(uint32_t t_lane, int c0, int c1, int n
     uint32_t pk[8];
 #pragma unroll
     for (int i = 0; i < 16; i += 2) {
-      float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), scale_log2, -m));
-      float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m));
+      float p0 = VT_EX2(fmaf(__uint_as_float(r[i]), scale_log2, -m));
+      float p1 = VT_EX2(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m));
       if (c + i >= nvalid) p0 = 0.f;
       if (c + i + 1 >= nvalid) p1 = 0.f;
       ps0 += p0;
@@ -218,7 +229,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     for (int s = 0; s < 2; ++s) {
       const uint32_t b0 = bar_base + 8u * (s * A_PER_SLOT);
       for (int i = 0; i < A_PER_SLOT; ++i)
-        mbar_init(b0 + 8u * i, (i == A_PFULL || i == A_OREAD || i == A_TURN) ? 256 : 1);
+        mbar_init(b0 + 8u * i, (i == A_OREAD || i == A_TURN) ? 256 : (i == A_PFULL || i == A_PFULL1) ? 128 : 1);
     }
     fence_barrier_init();
   }
@@ -321,21 +332,36 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
           if (j == nblk - 1) umma_commit(bar(A_QEMPTY));
         }
         __syncwarp();
-        // ---- O_j = P V_j : keys [0, cs) come from P0, keys [cs, nj) from P1
-        mbar_wait(bar(A_PFULL), ph);
+        // ---- O_j = P V_j : keys [0, cs) come from P0, keys [cs, nj) from P1.  The two column halves
+        // finish their exponentials at different times (96 vs 112 columns): the k steps over P0 are
+        // issued as soon as half 0 has arrived.
+        const uint32_t idesc_pv = make_idesc_bf16(kQTile, kDM, 0, 1);
+        const uint32_t idesc_t = make_idesc_bf16(kQTile, 16, 0, 1);
+        const uint64_t vd = make_desc_mnmajor_sw128(v_smem, 1024);
+        const uint64_t vtd = make_smem_desc(vt_smem, 256, 256, 6);   // MN-major, SWIZZLE_32B
+        const int ksteps = nj >> 4;
+        const int k0 = cs >> 4;
+        const uint32_t o_tmem = t_slot + out_col(cs, nj);
+        // O may only be written early where it cannot overlap scores half 1 has not consumed yet
+        const bool early_ok = (out_col(cs, nj) == 0) ? (cs >= kDH) : (nj <= 128);
         mbar_wait(bar(A_VFULL), ph);
+        mbar_wait(bar(A_PFULL), ph);
+        if (!early_ok) mbar_wait(bar(A_PFULL1), ph);
         tc_fence_after();
         if (elect_one_sync()) {
-          const uint32_t idesc = make_idesc_bf16(kQTile, kDM, 0, 1);
-          const uint32_t idesc_t = make_idesc_bf16(kQTile, 16, 0, 1);
-          const uint64_t vd = make_desc_mnmajor_sw128(v_smem, 1024);
-          const uint64_t vtd = make_smem_desc(vt_smem, 256, 256, 6);   // MN-major, SWIZZLE_32B
-          const int ksteps = nj >> 4;
-          const int k0 = cs >> 4;
-          const uint32_t o_tmem = t_slot + out_col(cs, nj);
-          for (int k = 0; k < ksteps; ++k) {   // 16 kv rows: 2048 B of the main tile, 512 B of the tail tile
-            const uint32_t a_tmem = (k < k0) ? (t_slot + kP0Col + 8 * k) : (t_slot + cs + 8 * (k - k0));
-            umma_ts(o_tmem, a_tmem, vd + 128 * k, idesc, k != 0 ? 1u : 0u);
+          for (int k = 0; k < k0; ++k) {   // 16 kv rows: 2048 B of the main tile, 512 B of the tail tile
+            const uint32_t a_tmem = t_slot + kP0Col + 8 * k;
+            umma_ts(o_tmem, a_tmem, vd + 128 * k, idesc_pv, k != 0 ? 1u : 0u);
+            if (kDT) umma_ts(o_tmem + kDM, a_tmem, vtd + 32 * k, idesc_t, k != 0 ? 1u : 0u);
+          }
+        }
+        __syncwarp();
+        if (early_ok) mbar_wait(bar(A_PFULL1), ph);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          for (int k = k0; k < ksteps; ++k) {
+            const uint32_t a_tmem = t_slot + cs + 8 * (k - k0);
+            umma_ts(o_tmem, a_tmem, vd + 128 * k, idesc_pv, k != 0 ? 1u : 0u);
             if (kDT) umma_ts(o_tmem + kDM, a_tmem, vtd + 32 * k, idesc_t, k != 0 ? 1u : 0u);
           }
           umma_commit(bar(A_OFULL));
@@ -374,6 +400,10 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       float o_acc[kHalfCols];
       float m_run = -INFINITY;
       float l_run = 0.f;      // this thread's partial row sum (its columns only)
+      // warp-uniform: all 32 query rows of this warp lie beyond the sequence (N = 197: the last quarter
+      // of every second tile).  Such a warp keeps every barrier protocol but skips the TMEM reads, the
+      // exponentials and the output (its P rows stay undefined; MMA rows are independent).
+      const bool live = qt * kQTile + quarter * 32 < p.N;
 
       for (int j = 0; j < nblk; ++j, ++step) {
         const uint32_t ph = step & 1u;
@@ -391,7 +421,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         tc_fence_after();
 
         // pass 1: partial row max, exchanged with the other half of the row
-        const float mx = row_max_part(t_lane, c0, c1, nvalid);
+        const float mx = live ? row_max_part(t_lane, c0, c1, nvalid) : 0.f;
         *my_x = mx;
         VT_TICK(1)
         named_bar_sync(bar_id, 256);
@@ -404,21 +434,30 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         // saturates the MUFU pipe, so the slots take turns: while one is here the other does its
         // MUFU-free work (row max, O fold, epilogue, MMA waits).  Single-block items only: the item
         // counts of the two slots differ by at most one, which the token protocol tolerates.
+#ifndef VT_A3_NOTURN
         if (nblk == 1 && !(g == 0 && it == 0))
           mbar_wait(bar(A_TURN), static_cast<uint32_t>(g == 0 ? it - 1 : it) & 1u);
+#endif
         VT_TICK(2)
-        const float psum = exp_part(t_lane, c0, c1, nvalid, p_col, p.scale_log2, m_new);
+        const float psum = live ? exp_part(t_lane, c0, c1, nvalid, p_col, p.scale_log2, m_new) : 1.f;
+#ifndef VT_A3_NOTURN
         if (nblk == 1) mbar_arrive(other_turn);
+#endif
         l_run = l_run * alpha + psum;
+        // partial row sum for the other half of the row: published before the arrive below, read
+        // after the A_OFULL wait of the last block (PV MMAs are issued only after both halves arrived)
+        if (j == nblk - 1) *my_l = l_run;
         tc_fence_before();
-        mbar_arrive(bar(A_PFULL));
+        mbar_arrive(bar(half ? A_PFULL1 : A_PFULL));
         VT_TICK(3)
 
         // O_j = P V_j lands in TMEM columns [0, 64): this thread folds its 32 output columns
         mbar_wait(bar(A_OFULL), ph);
         VT_TICK(4)
         tc_fence_after();
-        {
+        float l_other = 0.f;
+        if (j == nblk - 1) l_other = *other_l;
+        if (live) {
           uint32_t r[32];
           uint32_t r8[8];
           const uint32_t o_src = t_lane + out_col(cs, nj) + half * kHalfCols;
@@ -444,14 +483,32 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         tc_fence_before();
         mbar_arrive(bar(A_OREAD));
         VT_TICK(5)
+        if (j == nblk - 1) l_run += l_other;   // total row sum = both halves' partial sums
       }
+      if (!live) continue;
 
-      // total row sum = both halves' partial sums
-      *my_l = l_run;
-      named_bar_sync(bar_id, 256);
       float inv;
-      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(l_run + *other_l));
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(l_run));
 
+#ifdef VT_A3_DIRECT_STORE
+      // every thread owns kHalfCols contiguous bf16 of one output row: 16-byte global stores
+      {
+        const int row = qt * kQTile + row_in_tile;
+        if (row < p.N) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + img * p.out_batch_stride + row * p.out_row_stride +
+                                                head * kDH + half * kHalfCols);
+#pragma unroll
+          for (int jj = 0; jj < kHalfCols / 8; ++jj) {
+            uint4 o4;
+            o4.x = pack_bf16x2(o_acc[8 * jj + 0] * inv, o_acc[8 * jj + 1] * inv);
+            o4.y = pack_bf16x2(o_acc[8 * jj + 2] * inv, o_acc[8 * jj + 3] * inv);
+            o4.z = pack_bf16x2(o_acc[8 * jj + 4] * inv, o_acc[8 * jj + 5] * inv);
+            o4.w = pack_bf16x2(o_acc[8 * jj + 6] * inv, o_acc[8 * jj + 7] * inv);
+            dst[jj] = o4;
+          }
+        }
+      }
+#else
       // stage this warp's [32 rows x 32 columns] as a SWIZZLE_64B tile and TMA-store it
       if (lane == 0) tma_store_wait_read<0>();   // previous store out of this staging tile is done
       __syncwarp();
@@ -475,6 +532,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
                      : "memory");
         tma_store_commit();
       }
+#endif
       VT_TICK(6)
     }
     if (lane == 0) tma_store_wait<0>();
@@ -541,6 +599,9 @@ int attn3_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, in
   if (p.total_items >= (1LL << 31)) return VT_ERR_UNSUPPORTED;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.reverse = reverse;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.out_row_stride = out_row_stride;
+  p.out_batch_stride = out_batch_stride;
   p.dbg = g_attn3_dbg;
   const int smem = 1024 + 2 * slot_bytes_for(dh, p.bkv) + 8 * A_NBARS + 16 + 2 * (2 * 2 * kQTile * 4);
   if (smem > kSmemLimit) return VT_ERR_UNSUPPORTED;

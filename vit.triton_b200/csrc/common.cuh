@@ -83,16 +83,40 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   return done;
 }
 
+// try_wait with a suspend-time hint (ns): the warp sleeps in hardware until the phase completes or
+// the hint expires instead of returning after a few dozen cycles.
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return done;
+}
+
 // Bounded wait: a protocol bug must surface as a trapped kernel (a CUDA error the host sees),
-// never as a hung GPU.  ~4e9 cycles is about two seconds at boost clocks.
+// never as a hung GPU.  ~4e9 cycles is about two seconds at boost clocks.  The slow path must stay
+// cheap: a polling warp competes for issue slots with the warps doing the work (in the attention
+// kernel the un-hinted poll loop with a clock read per iteration was 24 % of all issued
+// instructions), so it sleeps on the suspend-time hint and looks at the clock every 256 polls.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("vt: mbarrier timeout block (%d,%d,%d) thread %d bar 0x%x parity %u\n", blockIdx.x,
-             blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
-      __trap();
+  long long t0 = 0;
+  uint32_t polls = 0;
+  while (!mbar_try_wait_hint(bar, parity, 1000000u)) {
+    if ((++polls & 255u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000LL) {
+        printf("vt: mbarrier timeout block (%d,%d,%d) thread %d bar 0x%x parity %u\n", blockIdx.x,
+               blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
+        __trap();
+      }
     }
   }
 }
