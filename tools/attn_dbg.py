@@ -27,11 +27,19 @@ for (B, H, N, dh) in shapes:
     flash_attention(qkv, H)
     torch.cuda.synchronize()
     lib.vt_debug_set_attn_buffer(None)
-    d = dbg.view(148, 2, 8).double()
     nq = (N + 127) // 128
-    n = B * H * nq / 296
-    names = ["wait-S", "pass1", "max-sync", "pass2", "wait-O", "O-read", "epilogue"]
-    print(f"B={B} H={H} N={N} dh={dh}: {us:.1f} us/launch (20 back-to-back); items/slot {n:.1f}")
-    for g in range(2):
-        print(f"   slot {g} per item cycles: " + ", ".join(f"{nm} {d[:, g, i].mean()/n:.0f}" for i, nm in enumerate(names))
-              + f", total {d[:, g, 7].mean()/n:.0f}")
+    impl = os.environ.get("VT_ATTN_IMPL", "4")
+    print(f"B={B} H={H} N={N} dh={dh}: {us:.1f} us/launch (20 back-to-back)")
+    if impl == "4" and dh == 64:
+        d = dbg.view(296, 8)[:148].double()
+        n = B * H * nq / 148
+        names = ["wait-S", "load+max", "max-sync", "exp", "wait-O", "O-fold", "epilogue"]
+        print(f"   items/CTA {n:.1f}; per item cycles: " + ", ".join(f"{nm} {d[:, i].mean()/n:.0f}" for i, nm in enumerate(names))
+              + f", total {d[:, 7].mean()/n:.0f}")
+    else:
+        d = dbg.view(148, 2, 8).double()
+        n = B * H * nq / 296
+        names = ["wait-S", "pass1", "max-sync", "pass2", "wait-O", "O-read", "epilogue"]
+        for g in range(2):
+            print(f"   slot {g} per item cycles: " + ", ".join(f"{nm} {d[:, g, i].mean()/n:.0f}" for i, nm in enumerate(names))
+                  + f", total {d[:, g, 7].mean()/n:.0f}")

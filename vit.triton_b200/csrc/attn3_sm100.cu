@@ -30,6 +30,7 @@
 // Head dim 80 (ViT-H): 160-byte rows do not fit the 128-byte swizzle, so every Q/K/V tile is loaded
 // as a 64-column SWIZZLE_128B part plus a 16-column SWIZZLE_32B part; QK^T gets a fifth K step on
 // the 32-byte tiles and P.V a second MMA (N = 16) per K step into output columns [64, 80).
+#include "attn_softmax.cuh"
 #include "common.cuh"
 #include "tensormap.h"
 
@@ -54,24 +55,12 @@ struct Attn3Params {
   long long total_items;
   int reverse;        // walk the items from the last to the first (L2 reuse, see api.cu)
   float scale_log2;
-  __nv_bfloat16* out;                          // direct-store epilogue (VT_A3_DIRECT_STORE)
-  long long out_row_stride, out_batch_stride;  // in elements
   long long* dbg;     // optional cycle counters (developer tool tools/attn_dbg.py)
 };
 
 enum { A_QFULL = 0, A_QEMPTY, A_KFULL, A_KEMPTY, A_VFULL, A_VEMPTY, A_SFULL, A_PFULL, A_PFULL1, A_OFULL,
        A_OREAD, A_TURN, A_PER_SLOT };   // A_PFULL / A_PFULL1: probabilities of column half 0 / 1 are in TMEM
 constexpr int A_NBARS = 2 * A_PER_SLOT;
-
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-  float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // column split of a block of nj score columns: first half owns [0, cs), second half [cs, nj)
 __device__ __forceinline__ int col_split(int nj) {
@@ -83,97 +72,6 @@ __device__ __forceinline__ int col_split(int nj) {
 // O_j (dh columns) must not overlap P1 = [cs, cs + (nj-cs)/2): columns [128, 128+dh) when P1 ends at or
 // before 128, else columns [0, dh) (then cs = 96 >= dh)
 __device__ __forceinline__ int out_col(int cs, int nj) { return (cs + ((nj - cs) >> 1) <= 128) ? 128 : 0; }
-
-// Row max over this thread's score columns [c0, c1) of which [c0, min(c1, nvalid_end)) are valid.
-__device__ __forceinline__ float row_max_part(uint32_t t_lane, int c0, int c1, int nvalid) {
-  float mx0 = -INFINITY, mx1 = -INFINITY;
-  int c = c0;
-  const int full_end = c0 + (((nvalid < c1 ? nvalid : c1) - c0) & ~31);   // end of fully valid 32-col chunks
-  for (; c + 64 <= full_end; c += 64) {
-    uint32_t ra[32], rb[32];
-    tmem_ld_32x32(t_lane + c, ra);
-    tmem_ld_32x32(t_lane + c + 32, rb);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      mx0 = fmax3(mx0, __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]));
-      mx1 = fmax3(mx1, __uint_as_float(rb[i]), __uint_as_float(rb[i + 1]));
-    }
-  }
-  for (; c < full_end; c += 32) {
-    uint32_t r[32];
-    tmem_ld_32x32(t_lane + c, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      mx0 = fmax3(mx0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-      mx1 = fmax3(mx1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-    }
-  }
-  for (; c < c1; c += 16) {
-    uint32_t r[16];
-    tmem_ld_32x16(t_lane + c, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (c + i < nvalid) mx0 = fmaxf(mx0, __uint_as_float(r[i]));
-  }
-  return fmaxf(mx0, mx1);
-}
-
-// p = exp2(s * scale - m) over this thread's columns [c0, c1); P (bf16x2) written to TMEM columns
-// p_col + (c - c0)/2; returns the partial row sum.  Next chunk's load is in flight during the math.
-#ifdef VT_A3_EXP_NOMUFU   // timing experiment: no MUFU in the exp pass (results wrong)
-#define VT_EX2(x) ((x) * 0.5f)
-#else
-#define VT_EX2(x) ex2_approx(x)
-#endif
-__device__ __forceinline__ float exp_part(uint32_t t_lane, int c0, int c1, int nvalid, uint32_t p_col,
-                                          float scale_log2, float m) {
-  float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
-  const int full_end = c0 + (((nvalid < c1 ? nvalid : c1) - c0) & ~31);
-  int c = c0;
-  for (; c < full_end; c += 32) {
-    uint32_t r[32];
-    tmem_ld_32x32(t_lane + c, r);
-    tmem_ld_wait();
-    uint32_t pk[16];
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      const float p0 = VT_EX2(fmaf(__uint_as_float(r[i + 0]), scale_log2, -m));
-      const float p1 = VT_EX2(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m));
-      const float p2 = VT_EX2(fmaf(__uint_as_float(r[i + 2]), scale_log2, -m));
-      const float p3 = VT_EX2(fmaf(__uint_as_float(r[i + 3]), scale_log2, -m));
-      ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
-      pk[(i >> 1) + 0] = pack_bf16x2(p0, p1);
-      pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
-    }
-#ifndef VT_A3_EXP_NOST
-    tmem_st_32x16(p_col + ((c - c0) >> 1), pk);
-#else
-    if (pk[3] == 0x12345u) tmem_st_32x16(p_col + ((c - c0) >> 1), pk);
-#endif
-  }
-  for (; c < c1; c += 16) {
-    uint32_t r[16];
-    tmem_ld_32x16(t_lane + c, r);
-    tmem_ld_wait();
-    uint32_t pk[8];
-#pragma unroll
-    for (int i = 0; i < 16; i += 2) {
-      float p0 = VT_EX2(fmaf(__uint_as_float(r[i]), scale_log2, -m));
-      float p1 = VT_EX2(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m));
-      if (c + i >= nvalid) p0 = 0.f;
-      if (c + i + 1 >= nvalid) p1 = 0.f;
-      ps0 += p0;
-      ps1 += p1;
-      pk[i >> 1] = pack_bf16x2(p0, p1);
-    }
-    tmem_st_32x8(p_col + ((c - c0) >> 1), pk);
-  }
-  tmem_st_wait();
-  return (ps0 + ps1) + (ps2 + ps3);
-}
 
 // shared-memory bytes of one slot: [Q main][K main][V main][Q tail][K tail][V tail][O staging]
 __host__ __device__ constexpr int slot_bytes_for(int dh, int bkv) {
@@ -434,15 +332,11 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         // saturates the MUFU pipe, so the slots take turns: while one is here the other does its
         // MUFU-free work (row max, O fold, epilogue, MMA waits).  Single-block items only: the item
         // counts of the two slots differ by at most one, which the token protocol tolerates.
-#ifndef VT_A3_NOTURN
         if (nblk == 1 && !(g == 0 && it == 0))
           mbar_wait(bar(A_TURN), static_cast<uint32_t>(g == 0 ? it - 1 : it) & 1u);
-#endif
         VT_TICK(2)
         const float psum = live ? exp_part(t_lane, c0, c1, nvalid, p_col, p.scale_log2, m_new) : 1.f;
-#ifndef VT_A3_NOTURN
         if (nblk == 1) mbar_arrive(other_turn);
-#endif
         l_run = l_run * alpha + psum;
         // partial row sum for the other half of the row: published before the arrive below, read
         // after the A_OFULL wait of the last block (PV MMAs are issued only after both halves arrived)
@@ -490,25 +384,6 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       float inv;
       asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(l_run));
 
-#ifdef VT_A3_DIRECT_STORE
-      // every thread owns kHalfCols contiguous bf16 of one output row: 16-byte global stores
-      {
-        const int row = qt * kQTile + row_in_tile;
-        if (row < p.N) {
-          uint4* dst = reinterpret_cast<uint4*>(p.out + img * p.out_batch_stride + row * p.out_row_stride +
-                                                head * kDH + half * kHalfCols);
-#pragma unroll
-          for (int jj = 0; jj < kHalfCols / 8; ++jj) {
-            uint4 o4;
-            o4.x = pack_bf16x2(o_acc[8 * jj + 0] * inv, o_acc[8 * jj + 1] * inv);
-            o4.y = pack_bf16x2(o_acc[8 * jj + 2] * inv, o_acc[8 * jj + 3] * inv);
-            o4.z = pack_bf16x2(o_acc[8 * jj + 4] * inv, o_acc[8 * jj + 5] * inv);
-            o4.w = pack_bf16x2(o_acc[8 * jj + 6] * inv, o_acc[8 * jj + 7] * inv);
-            dst[jj] = o4;
-          }
-        }
-      }
-#else
       // stage this warp's [32 rows x 32 columns] as a SWIZZLE_64B tile and TMA-store it
       if (lane == 0) tma_store_wait_read<0>();   // previous store out of this staging tile is done
       __syncwarp();
@@ -532,7 +407,6 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
                      : "memory");
         tma_store_commit();
       }
-#endif
       VT_TICK(6)
     }
     if (lane == 0) tma_store_wait<0>();
@@ -599,9 +473,6 @@ int attn3_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, in
   if (p.total_items >= (1LL << 31)) return VT_ERR_UNSUPPORTED;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.reverse = reverse;
-  p.out = static_cast<__nv_bfloat16*>(out);
-  p.out_row_stride = out_row_stride;
-  p.out_batch_stride = out_batch_stride;
   p.dbg = g_attn3_dbg;
   const int smem = 1024 + 2 * slot_bytes_for(dh, p.bkv) + 8 * A_NBARS + 16 + 2 * (2 * 2 * kQTile * 4);
   if (smem > kSmemLimit) return VT_ERR_UNSUPPORTED;
