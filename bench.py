@@ -177,6 +177,9 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="bracket ONE extra step after the timed region with cudaProfilerStart/Stop "
+                         "(ncu --profile-from-start off then captures exactly one forward)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -265,6 +268,13 @@ def main():
         sync_all()
         clocks = sampler.stop() if rank == 0 else None
         launches = _lib.launch_count - launches0
+    if args.profile_step:
+        with torch.no_grad():
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            step(dev_inputs[0])
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
     ms_total = start.elapsed_time(stop)
     gemm_ms = sum(gemm_events[i].elapsed_time(gemm_events[i + 1]) for i in range(0, len(gemm_events), 2))
     n_gemm = len(gemm_events) // 2
