@@ -246,58 +246,78 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const Patc
     const long long out_row = static_cast<long long>(e_img) * n_tok + 1 + e_patch;
     const float* posb_row = p.posb + static_cast<long long>(1 + e_patch) * p.D;
 
+    // 16 columns per step; the position/bias values of the NEXT step are loaded before this step's
+    // accumulator columns are read and stored (the epilogue was latency-bound on these loads: half
+    // of all stall samples, profiles/r01d), and the first step's loads are issued before the
+    // accumulator is even complete.
+    constexpr int kStep = 16;
+    const int col_base = n_blk * PE_BN + chalf * (PE_BN / 2);
+    auto load_posb = [&](float4 (&pb)[4], int col) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e_valid) {
+          const int c4 = col + 4 * i;
+          if (c4 + 3 < p.D) {
+            pb[i] = __ldg(reinterpret_cast<const float4*>(posb_row + c4));
+          } else {
+            if (c4 + 0 < p.D) pb[i].x = posb_row[c4 + 0];
+            if (c4 + 1 < p.D) pb[i].y = posb_row[c4 + 1];
+            if (c4 + 2 < p.D) pb[i].z = posb_row[c4 + 2];
+          }
+        }
+      }
+    };
+    float4 pb_cur[4], pb_nxt[4];
+    load_posb(pb_cur, col_base);
     mbar_wait(acc_bar, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int cc = 0; cc < PE_BN / 2; cc += 32) {
+    for (int cc = 0; cc < PE_BN / 2; cc += kStep) {
       const int c = chalf * (PE_BN / 2) + cc;
       const int col = n_blk * PE_BN + c;
-      uint32_t rr[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c, rr);
+      uint32_t rr[16];
+      tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c, rr);
+      if (cc + kStep < PE_BN / 2) load_posb(pb_nxt, col + kStep);
       tmem_ld_wait();
-      if (!e_valid || col >= p.D) continue;
-      float v[32];
+      if (e_valid && col < p.D) {
+        float v[16];
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (col + i + 3 < p.D) {
-          pb = __ldg(reinterpret_cast<const float4*>(posb_row + col + i));
-        } else {
-          if (col + i + 0 < p.D) pb.x = posb_row[col + i + 0];
-          if (col + i + 1 < p.D) pb.y = posb_row[col + i + 1];
-          if (col + i + 2 < p.D) pb.z = posb_row[col + i + 2];
+        for (int i = 0; i < 4; ++i) {
+          v[4 * i + 0] = __uint_as_float(rr[4 * i + 0]) + pb_cur[i].x;
+          v[4 * i + 1] = __uint_as_float(rr[4 * i + 1]) + pb_cur[i].y;
+          v[4 * i + 2] = __uint_as_float(rr[4 * i + 2]) + pb_cur[i].z;
+          v[4 * i + 3] = __uint_as_float(rr[4 * i + 3]) + pb_cur[i].w;
         }
-        v[i + 0] = __uint_as_float(rr[i + 0]) + pb.x;
-        v[i + 1] = __uint_as_float(rr[i + 1]) + pb.y;
-        v[i + 2] = __uint_as_float(rr[i + 2]) + pb.z;
-        v[i + 3] = __uint_as_float(rr[i + 3]) + pb.w;
-      }
-      const bool full_chunk = col + 32 <= p.D;
-      if (p.out_f32) {
-        float* o = static_cast<float*>(p.out) + out_row * p.D + col;
-        if (full_chunk) {
+        const bool full_chunk = col + kStep <= p.D;
+        if (p.out_f32) {
+          float* o = static_cast<float*>(p.out) + out_row * p.D + col;
+          if (full_chunk) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        } else {
-          for (int i = 0; i < 32 && col + i < p.D; ++i) o[i] = v[i];
-        }
-      } else {
-        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + out_row * p.D + col;
-        if (full_chunk) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 o4;
-            o4.x = pack_bf16x2(v[i + 0], v[i + 1]);
-            o4.y = pack_bf16x2(v[i + 2], v[i + 3]);
-            o4.z = pack_bf16x2(v[i + 4], v[i + 5]);
-            o4.w = pack_bf16x2(v[i + 6], v[i + 7]);
-            *reinterpret_cast<uint4*>(o + i) = o4;
+            for (int i = 0; i < 16; i += 4)
+              *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+            for (int i = 0; i < 16 && col + i < p.D; ++i) o[i] = v[i];
           }
         } else {
-          for (int i = 0; i < 32 && col + i < p.D; ++i) o[i] = __float2bfloat16_rn(v[i]);
+          __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + out_row * p.D + col;
+          if (full_chunk) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 8) {
+              uint4 o4;
+              o4.x = pack_bf16x2(v[i + 0], v[i + 1]);
+              o4.y = pack_bf16x2(v[i + 2], v[i + 3]);
+              o4.z = pack_bf16x2(v[i + 4], v[i + 5]);
+              o4.w = pack_bf16x2(v[i + 6], v[i + 7]);
+              *reinterpret_cast<uint4*>(o + i) = o4;
+            }
+          } else {
+            for (int i = 0; i < 16 && col + i < p.D; ++i) o[i] = __float2bfloat16_rn(v[i]);
+          }
         }
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pb_cur[i] = pb_nxt[i];
     }
 
     // CLS rows: the first row-tile of every column block writes cls + pos[0] for all images.
