@@ -31,7 +31,7 @@ typedef enum {
   VT_ERR_DRIVER = -5       /* cuTensorMapEncodeTiled unavailable / failed */
 } vt_status;
 
-typedef enum { VT_F32 = 0, VT_BF16 = 1 } vt_dtype;
+typedef enum { VT_F32 = 0, VT_BF16 = 1, VT_U8 = 2 /* pixels of vt_patch_embed only */ } vt_dtype;
 
 /* Library version (major*10000 + minor*100 + patch). */
 int vt_version(void);
@@ -99,9 +99,12 @@ int vt_flash_attn(const void* q, const void* k, const void* v, void* out, int32_
                   int64_t out_row_stride, int64_t out_batch_stride, float scale, void* stream);
 
 /* K2 — patch embedding (im2col-free tcgen05 GEMM) with CLS + position embedding fused:
- * pixels [B,C,S,S] (pix_dtype f32|bf16); w [D, C*P*P] bf16 (row stride ldw); posb [n+1, D] f32 =
- * pos + (row 0: cls, rows >= 1: conv bias); out [B, n+1, D] (out_dtype).
- * Replaces Conv2DTriton.forward + Embeddings.forward glue (conv2d.py:100-167, vit/vit.py:188-200). */
+ * pixels [B,C,S,S] (pix_dtype f32|bf16) with w [D, C*P*P] bf16 in (c,i,j) order (row stride ldw), or
+ * pixels [B,S,S,C] (pix_dtype VT_U8: raw NHWC bytes) with w in (i,j,c) order — the caller folds the
+ * image processor's rescale / mean / std into w and posb (vit/packing.py:pack_embeddings_u8);
+ * posb [n+1, D] f32 = pos + (row 0: cls, rows >= 1: conv bias); out [B, n+1, D] (out_dtype).
+ * Replaces Conv2DTriton.forward + Embeddings.forward glue (conv2d.py:100-167, vit/vit.py:188-200);
+ * the uint8 form also replaces the HF ViTImageProcessor rescale + normalise step in front of it. */
 int vt_patch_embed(const void* pixels, int32_t pix_dtype, const void* w, int64_t ldw,
                    const float* posb, void* out, int32_t out_dtype, int32_t B, int32_t C, int32_t S,
                    int32_t P, int32_t D, void* stream);

@@ -307,6 +307,33 @@ def test_patch_embed_fused(S, P, D, B, pix_dtype):
     assert (got.float() - want).abs().max().item() <= 0.05
 
 
+@pytest.mark.parametrize("S,P,D,B", [(224, 16, 768, 3), (64, 16, 128, 5), (56, 14, 160, 2), (224, 14, 1280, 1), (96, 32, 64, 2)])
+def test_patch_embed_uint8_nhwc(S, P, D, B):
+    """Raw uint8 NHWC pixels with the image processor's rescale / normalise folded into the operands
+    == conv2d over the normalised NCHW pixels (8-byte vector gather for P*3 % 8 == 0, scalar otherwise)."""
+    from vit.vit import Embeddings
+    n = (S // P) ** 2
+    emb = Embeddings(P, n, 3 * P * P, D).to(dev())
+    with torch.no_grad():
+        for p_ in emb.parameters():
+            p_.copy_(torch.randn_like(p_) * 0.05)
+    emb = emb.to(torch.bfloat16)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    x = torch.randint(0, 256, (B, S, S, 3), device=dev(), dtype=torch.uint8)
+    got = emb.forward_uint8(x, mean, std, 1.0 / 255.0)
+    xn = (x.float() / 255.0 - torch.tensor(mean, device=dev())) / torch.tensor(std, device=dev())
+    tok = F.conv2d(xn.permute(0, 3, 1, 2), emb.projection.weight.float(), emb.projection.bias.float(), stride=P)
+    tok = tok.flatten(2).transpose(1, 2)
+    want = torch.cat([emb.cls_token.float().expand(B, -1, -1), tok], 1) + emb.position_embeddings.float()
+    assert got.shape == (B, n + 1, D) and got.dtype == torch.bfloat16
+    assert rel_err(got, want) <= 2 ** -7, f"rel err {rel_err(got, want)}"
+    # second call hits the packing cache; changing a weight invalidates it
+    assert torch.equal(emb.forward_uint8(x, mean, std, 1.0 / 255.0), got)
+    with torch.no_grad():
+        emb.projection.bias.add_(1.0)
+    assert not torch.equal(emb.forward_uint8(x, mean, std, 1.0 / 255.0), got)
+
+
 def test_pool_cls():
     from vit.kernels import _lib
     x = torch.randn(5, 197, 768, device=dev()).bfloat16()

@@ -181,3 +181,46 @@ def test_c4_c5_architectures_bf16_match_hf(arch):
     assert torch.isfinite(got).all()
     assert _cos(got, want) >= 0.999, f"cosine {_cos(got, want)}"
     assert (got - want).abs().max().item() <= 0.2, f"max-abs {(got - want).abs().max().item()}"
+
+
+def test_uint8_nhwc_input_matches_hf_image_processor_path():
+    """Row f4 of SURVEY.md section 8: raw uint8 NHWC pixels in, the HF ViTImageProcessor arithmetic
+    (rescale 1/255, mean 0.5, std 0.5) folded into the patch-embedding kernel.  Oracle: the same
+    arithmetic in fp32 on the CPU followed by HF ViTModel."""
+    model, hf = _build("vit-b16-224", torch.bfloat16)
+    g = torch.Generator().manual_seed(7)
+    x_u8 = torch.randint(0, 256, (3, 224, 224, 3), generator=g, dtype=torch.uint8)
+    pixel_values = ((x_u8.float() * (1.0 / 255.0)) - 0.5) / 0.5
+    want = hf_oracle.hf_forward(hf, pixel_values.permute(0, 3, 1, 2).contiguous())
+    with torch.no_grad():
+        got = model.forward_uint8(x_u8.to(DEV)).float().cpu()
+        ref_path = model(pixel_values.permute(0, 3, 1, 2).contiguous().to(DEV, torch.bfloat16)).float().cpu()
+        pooled = model.pooled(x_u8.to(DEV)).float().cpu()
+    assert torch.isfinite(got).all()
+    assert _cos(got, want) >= 0.999, f"cosine {_cos(got, want)}"
+    assert (got - want).abs().max().item() <= 0.15, f"max-abs {(got - want).abs().max().item()}"
+    assert _cos(got, ref_path) >= 0.9995
+    assert torch.equal(pooled, got[:, 0, :].bfloat16().float())
+
+
+def test_pooler_head_matches_hf_pooler():
+    """Row f2: HF ViTModel(add_pooling_layer=True).pooler_output == VIT(add_pooling_layer=True).pooler_output."""
+    from transformers import ViTConfig, ViTModel
+    from vit.utils import transfer_pretrained_weights
+    from vit.vit import VIT
+    arch = "tiny-b"
+    torch.manual_seed(3)
+    hf = ViTModel(ViTConfig(**hf_oracle.ARCHS[arch]), add_pooling_layer=True).eval()
+    with torch.no_grad():
+        hf.pooler.dense.bias.copy_(torch.randn_like(hf.pooler.dense.bias) * 0.1)
+    x = hf_oracle.make_input(arch, 5)
+    with torch.no_grad():
+        want = hf(pixel_values=x).pooler_output
+    for dtype, tol in ((torch.float32, 1e-4), (torch.bfloat16, 3e-2)):
+        model = VIT(**hf_oracle.vit_kwargs(arch), add_pooling_layer=True)
+        transfer_pretrained_weights(hf, model, verbose=False)
+        model = model.to(DEV, dtype).eval()
+        with torch.no_grad():
+            got = model.pooler_output(x.to(DEV, dtype)).float().cpu()
+        assert got.shape == want.shape
+        assert (got - want).abs().max().item() <= tol, f"{dtype}: max-abs {(got - want).abs().max().item()}"

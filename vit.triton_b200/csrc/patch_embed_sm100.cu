@@ -8,6 +8,11 @@
 // channel, output row), scalar tl.sum, every patch re-read D times) plus the torch glue after it
 // (flatten/transpose, cat(cls), + position_embeddings: vit/vit.py:190-200).
 //
+// Pixel formats: NCHW fp32 / bf16 with k = (c, i, j) — the reference's layout — and NHWC uint8 with
+// k = (i, j, c) (camera / decoder output: the ViTImageProcessor rescale + normalise is folded into
+// the packed weights and the bias table on the host, so the kernel only widens bytes to bf16,
+// which is exact for 0..255).
+//
 // A (the patches) is never materialised: four producer warps gather 128 patches x 64 k straight
 // from the NCHW pixels into the SWIZZLE_128B K-major smem layout the UMMA descriptor expects
 // (TMA cannot express a 14-pixel, 28-byte inner box, and C=3 rules out im2col-mode TMA).
@@ -52,6 +57,11 @@ struct PatchParams {
 
 __device__ __forceinline__ float px_to_f(float v) { return v; }
 __device__ __forceinline__ float px_to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float px_to_f(uint8_t v) { return static_cast<float>(v); }
+// byte b of w as an exact float: 0x4B0000bb is 2^23 + b
+__device__ __forceinline__ float byte_to_f(uint32_t w, int b) {
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 + b)) - 8388608.0f;
+}
 
 // Raw (unconverted) pixels of one 8-element K chunk, as loaded: converting at load time would make
 // the thread wait for the load and defeat the prefetch ring.
@@ -76,12 +86,22 @@ struct RawChunk<float, true> {
     return make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
   }
 };
+template <>
+struct RawChunk<uint8_t, true> {
+  uint2 v;
+  __device__ __forceinline__ void zero() { v = make_uint2(0u, 0u); }
+  __device__ __forceinline__ void load(const uint8_t* src) { v = __ldg(reinterpret_cast<const uint2*>(src)); }
+  __device__ __forceinline__ uint4 packed() const {
+    return make_uint4(pack_bf16x2(byte_to_f(v.x, 0), byte_to_f(v.x, 1)), pack_bf16x2(byte_to_f(v.x, 2), byte_to_f(v.x, 3)),
+                      pack_bf16x2(byte_to_f(v.y, 0), byte_to_f(v.y, 1)), pack_bf16x2(byte_to_f(v.y, 2), byte_to_f(v.y, 3)));
+  }
+};
 template <typename TPix>
 struct RawChunk<TPix, false> {
   TPix e[8];
   __device__ __forceinline__ void zero() {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) e[i] = TPix(0.f);
+    for (int i = 0; i < 8; ++i) e[i] = TPix(0);
   }
   __device__ __forceinline__ uint4 packed() const {
     return make_uint4(pack_bf16x2(px_to_f(e[0]), px_to_f(e[1])), pack_bf16x2(px_to_f(e[2]), px_to_f(e[3])),
@@ -92,7 +112,7 @@ struct RawChunk<TPix, false> {
 template <typename TPix, bool kVec>
 __global__ void __launch_bounds__(PE_THREADS, 2)
 patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const PatchParams p) {
-  constexpr int NPF = (kVec && sizeof(TPix) == 2) ? 3 : 2;   // K blocks of pixel loads in flight
+  constexpr int NPF = (kVec && sizeof(TPix) <= 2) ? 3 : 2;   // K blocks of pixel loads in flight
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -173,10 +193,13 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const Patc
     const int patch = row_valid ? static_cast<int>(m - static_cast<long long>(img) * p.n_patches) : 0;
     const int py = patch / p.grid_w;
     const int px = patch - py * p.grid_w;
+    constexpr bool kNHWC = sizeof(TPix) == 1;   // uint8 pixels are [B, S, S, C], k = (i, j, c)
     const TPix* img_base = static_cast<const TPix*>(p.pixels) +
                            static_cast<long long>(img) * p.C * p.S * p.S +
-                           static_cast<long long>(py) * p.P * p.S + px * p.P;
+                           (kNHWC ? (static_cast<long long>(py) * p.P * p.S + px * p.P) * p.C
+                                  : static_cast<long long>(py) * p.P * p.S + px * p.P);
     const int PP = p.P * p.P;
+    const int PC = p.P * p.C;
 
     RawChunk<TPix, kVec> ring[NPF][4];
     auto issue_loads = [&](RawChunk<TPix, kVec> (&dst)[4], int kb) {
@@ -185,7 +208,11 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const Patc
         const int k0 = kb * PE_BK + (hh * 4 + ch) * 8;
         dst[ch].zero();
         if (row_valid && k0 < p.K) {
-          if constexpr (kVec) {
+          if constexpr (kVec && kNHWC) {
+            const int i = k0 / PC;          // patch row; the 8 bytes stay inside it: (P*C) % 8 == 0
+            const int rem = k0 - i * PC;
+            dst[ch].load(img_base + static_cast<long long>(i) * p.S * p.C + rem);
+          } else if constexpr (kVec) {
             const int c = k0 / PP;
             const int rem = k0 - c * PP;
             const int i = rem / p.P;
@@ -196,11 +223,17 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const Patc
             for (int e = 0; e < 8; ++e) {
               const int k = k0 + e;
               if (k < p.K) {
-                const int c = k / PP;
-                const int rem = k - c * PP;
-                const int i = rem / p.P;
-                const int j = rem - i * p.P;
-                dst[ch].e[e] = img_base[(static_cast<long long>(c) * p.S + i) * p.S + j];
+                if constexpr (kNHWC) {
+                  const int i = k / PC;
+                  const int rem = k - i * PC;   // j * C + c
+                  dst[ch].e[e] = img_base[static_cast<long long>(i) * p.S * p.C + rem];
+                } else {
+                  const int c = k / PP;
+                  const int rem = k - c * PP;
+                  const int i = rem / p.P;
+                  const int j = rem - i * p.P;
+                  dst[ch].e[e] = img_base[(static_cast<long long>(c) * p.S + i) * p.S + j];
+                }
               }
             }
           }
@@ -360,8 +393,9 @@ int launch_patch(const CUtensorMap& tw, const PatchParams& p, dim3 grid, cudaStr
 
 }  // namespace
 
-// pixels [B,C,S,S] (fp32 or bf16), w [D, C*P*P] bf16 with row stride ldw (elements, multiple of 8),
-// posb [n+1, D] fp32, out [B, n+1, D] bf16|f32.
+// pixels [B,C,S,S] (fp32 or bf16, k = (c,i,j)) or [B,S,S,C] (uint8, k = (i,j,c)); w [D, C*P*P] bf16 in
+// the matching k order with row stride ldw (elements, multiple of 8), posb [n+1, D] fp32,
+// out [B, n+1, D] bf16|f32.
 int patch_embed_tcgen05(const void* pixels, int pix_dtype, const void* w, long long ldw,
                         const float* posb, void* out, int out_dtype, int B, int C, int S, int P,
                         int D, cudaStream_t stream) {
@@ -398,6 +432,11 @@ int patch_embed_tcgen05(const void* pixels, int pix_dtype, const void* w, long l
   if (pix_dtype == VT_BF16)
     return vec ? launch_patch<__nv_bfloat16, true>(tw, p, grid, stream)
                : launch_patch<__nv_bfloat16, false>(tw, p, grid, stream);
+  if (pix_dtype == VT_U8) {
+    // 8-byte loads: every patch row (P*C bytes) and every image row (S*C bytes) is a multiple of 8
+    const bool vec8 = ((P * C) % 8 == 0) && ((S * C) % 8 == 0);
+    return vec8 ? launch_patch<uint8_t, true>(tw, p, grid, stream) : launch_patch<uint8_t, false>(tw, p, grid, stream);
+  }
   return VT_ERR_DTYPE;
 }
 

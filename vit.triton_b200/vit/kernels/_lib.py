@@ -15,6 +15,7 @@ _lib: Optional[ctypes.CDLL] = None
 
 VT_F32 = 0
 VT_BF16 = 1
+VT_U8 = 2     # raw NHWC pixels of vt_patch_embed
 
 _c_i32 = ctypes.c_int32
 _c_i64 = ctypes.c_int64

@@ -120,6 +120,68 @@ def pack_embeddings(emb) -> SimpleNamespace:
                            bias32=emb.projection.bias.detach().float().contiguous())
 
 
+def pack_embeddings_u8(emb, image_mean, image_std, rescale_factor: float) -> SimpleNamespace:
+    """Patch projection for RAW uint8 NHWC pixels: the image processor's
+    ``(x * rescale_factor - mean_c) / std_c`` (HF ViTImageProcessor: 1/255, 0.5, 0.5) is folded into
+    the operands, so the kernel multiplies bytes:
+
+        sum_k w[d,k] * (x_k * r - mean_c) / std_c  =  sum_k (w[d,k] * r / std_c) * x_k  -  sum_k w[d,k] * mean_c / std_c
+
+    The weight is re-ordered from the reference's (c, i, j) to (i, j, c) — a patch row of an NHWC
+    image is P*C contiguous bytes — and scaled in fp32 before the single rounding to bf16; the
+    constant term joins the conv bias in the fp32 position/bias table."""
+    w = emb.projection.weight.detach().float()                 # [D, C, P, P]
+    D, C = w.shape[0], w.shape[1]
+    mean = torch.as_tensor(image_mean, dtype=torch.float32, device=w.device).reshape(1, C, 1, 1)
+    std = torch.as_tensor(image_std, dtype=torch.float32, device=w.device).reshape(1, C, 1, 1)
+    w_scaled = w * (float(rescale_factor) / std)
+    offset = (w * (mean / std)).sum(dim=(1, 2, 3))              # [D]
+    K = w[0].numel()
+    kpad = (K + 7) // 8 * 8
+    w2d = torch.zeros((D, kpad), device=w.device, dtype=emb.projection.weight.dtype)
+    w2d[:, :K] = w_scaled.permute(0, 2, 3, 1).reshape(D, K).to(w2d.dtype)
+    pos = emb.position_embeddings.detach().float()[0]
+    posb = pos.clone()
+    posb[0] += emb.cls_token.detach().float().reshape(-1)
+    posb[1:] += emb.projection.bias.detach().float() - offset
+    return SimpleNamespace(w=w2d, ldw=kpad, K=K, posb=posb.contiguous())
+
+
+def patch_embed_u8(emb, x: torch.Tensor, image_mean, image_std, rescale_factor: float) -> torch.Tensor:
+    """Raw uint8 NHWC pixels (B, S, S, C) -> token embeddings (B, n+1, D), rescale + normalise + patch
+    projection + CLS + position embeddings in ONE kernel (bf16 models on the tensor-core path)."""
+    w = emb.projection.weight
+    assert x.is_cuda and x.dtype == torch.uint8 and x.dim() == 4, \
+        f"Raw pixels need to be a CUDA uint8 (B, H, W, C) tensor, provided: {x.dtype}, {tuple(x.shape)}"
+    assert w.dtype == torch.bfloat16 and emb.hidden_dim % 8 == 0, \
+        "The fused uint8 input path runs on the bf16 tensor-core kernels only"
+    B, S, S2, C = x.shape
+    assert S == S2 and C == emb.channels, f"Image size {tuple(x.shape[1:])} not matching with the model input size"
+    key = (tuple(float(m) for m in image_mean), tuple(float(v) for v in image_std), float(rescale_factor))
+    cache = emb.__dict__.setdefault("_u8_pack", {})
+    params = emb._packed_sources()
+    stamp = emb._packed_key(params)
+    hit = cache.get(key)
+    if hit is None or hit[0] != stamp:
+        with torch.no_grad():
+            hit = (stamp, pack_embeddings_u8(emb, image_mean, image_std, rescale_factor))
+        cache.clear()
+        cache[key] = hit
+    pk = hit[1]
+    x = x.contiguous()
+    n_tok = emb.num_patches + 1
+    out = torch.empty((B, n_tok, emb.hidden_dim), device=x.device, dtype=w.dtype)
+    if B == 0:
+        return out
+    stream = _lib.stream_ptr(x)
+    step = 65535 * 128 // emb.num_patches
+    for b0 in range(0, B, step):
+        nb = min(step, B - b0)
+        _lib.call("vt_patch_embed", x[b0:].data_ptr(), _lib.VT_U8, pk.w.data_ptr(), pk.ldw, pk.posb.data_ptr(),
+                  out[b0:].data_ptr(), _lib.VT_BF16, nb, C, S, emb.patch_size, emb.hidden_dim, stream)
+    return out
+
+
 def folding_supported(x: torch.Tensor, dim: int, mlp_dim: int) -> bool:
     """LayerNorm folding runs on the bf16 tensor-core GEMM only."""
     return x.is_cuda and x.dtype == torch.bfloat16 and dim % 64 == 0 and mlp_dim % 8 == 0

@@ -250,11 +250,34 @@ class Embeddings(packing.PackedMixin, nn.Module):
             return out
         return packing.patch_embed(self, x)
 
+    def forward_uint8(self, x, image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5),
+                      rescale_factor: float = 1.0 / 255.0) -> torch.Tensor:
+        """Raw uint8 NHWC pixels (B, H, W, C) -> embeddings: the image processor's rescale and
+        normalisation (defaults: HF ``ViTImageProcessor`` of google/vit-base-patch16-224) are folded
+        into the patch projection, see ``packing.pack_embeddings_u8``."""
+        return packing.patch_embed_u8(self, x, image_mean, image_std, rescale_factor)
+
     def _packed_sources(self):
         return [self.cls_token, self.position_embeddings, self.projection.weight, self.projection.bias]
 
     def _build_packed(self):
         return packing.pack_embeddings(self)
+
+
+class Pooler(nn.Module):
+    """HF ``ViTPooler`` (modeling_vit.py:461-474): tanh(dense(CLS hidden state)).  The reference's
+    loader already maps ``pooler.dense.{weight,bias}`` (vit/utils.py:63-64) but the reference model has
+    no such module; ``VIT(..., add_pooling_layer=True)`` adds it.  The dense layer runs through the same
+    ``matmul`` entry point as every other dense layer (tensor-core GEMM for bf16); weight is (in, out)."""
+
+    def __init__(self, hidden_dim: int):
+        super().__init__()
+        self.dense = LinearWithBias(hidden_dim, hidden_dim)
+
+    def forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
+        cls = hidden_states[:, :1, :]                       # (B, 1, D) view: matmul takes any strides
+        out = self.dense(cls if cls.is_contiguous() else cls.contiguous())
+        return torch.tanh(out[:, 0, :])
 
 
 class VIT(nn.Module):
@@ -271,6 +294,7 @@ class VIT(nn.Module):
         num_heads: int,
         num_layers: int,
         mlp_dim: Optional[int] = None,
+        add_pooling_layer: bool = False,
     ):
         super().__init__()
         assert height == width, "Height and width should be the same"
@@ -296,6 +320,8 @@ class VIT(nn.Module):
         self.encoder = Encoder(num_layers=self.num_layers, num_heads=self.num_heads, hidden_dim=self.hidden_dim,
                                d_out=d_out, mlp_dim=mlp_dim)
         self.layernorm = LayerNormTriton(dim=self.hidden_dim, eps=1e-12)
+        # optional HF pooler (tanh(dense(CLS))): state-dict keys pooler.dense.{weight,bias}
+        self.pooler = Pooler(self.hidden_dim) if add_pooling_layer else None
 
     @property
     def device(self) -> torch.device:
@@ -312,9 +338,27 @@ class VIT(nn.Module):
         x = self.layernorm(x)
         return x
 
+    def forward_uint8(self, x, image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5),
+                      rescale_factor: float = 1.0 / 255.0):
+        """Forward from RAW uint8 NHWC pixels (B, H, W, C) — the step in front of the reference's
+        ``forward``: rescale + normalise (HF ``ViTImageProcessor``) run inside the patch-embedding
+        kernel, so the host -> device copy is one byte per pixel value."""
+        assert tuple(x.shape[1:]) == (self.height, self.width, self.channels), f"Image size {x.shape[1:]} not matching with the model input size: {self.height, self.width, self.channels}"
+        x = self.embeddings.forward_uint8(x, image_mean, image_std, rescale_factor)
+        x = self.encoder(x)
+        x = self.layernorm(x)
+        return x
+
+    def pooler_output(self, x) -> torch.Tensor:
+        """HF ``ViTModel(...).pooler_output``: tanh(dense(final hidden state of CLS)), (B, D)."""
+        assert self.pooler is not None, "Model was built without add_pooling_layer=True"
+        hidden = self.forward_uint8(x) if x.dtype == torch.uint8 else self.forward(x)
+        return self.pooler(hidden)
+
     def pooled(self, x) -> torch.Tensor:
-        """CLS row of the final hidden states, (B, D): the tensor the data-parallel wrapper gathers."""
-        hidden = self.forward(x)
+        """CLS row of the final hidden states, (B, D): the tensor the data-parallel wrapper gathers.
+        uint8 (B, H, W, C) inputs take the fused raw-pixel path."""
+        hidden = self.forward_uint8(x) if x.dtype == torch.uint8 else self.forward(x)
         out = torch.empty((hidden.shape[0], hidden.shape[2]), device=hidden.device, dtype=hidden.dtype)
         _lib.call("vt_pool_cls", hidden.data_ptr(), out.data_ptr(), hidden.shape[0], hidden.shape[2],
                   hidden.stride(0), _lib.dtype_code(hidden), _lib.stream_ptr(hidden))
