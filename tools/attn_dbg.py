@@ -28,7 +28,7 @@ for (B, H, N, dh) in shapes:
     torch.cuda.synchronize()
     lib.vt_debug_set_attn_buffer(None)
     nq = (N + 127) // 128
-    impl = os.environ.get("VT_ATTN_IMPL", "4")
+    impl = os.environ.get("VT_ATTN_IMPL", "5")
     print(f"B={B} H={H} N={N} dh={dh}: {us:.1f} us/launch (20 back-to-back)")
     if impl == "4" and dh == 64:
         d = dbg.view(296, 8)[:148].double()

@@ -21,6 +21,7 @@ void gemm2_set_debug_buffer(void*);
 void attn2_set_debug_buffer(void*);
 void attn3_set_debug_buffer(void*);
 void attn4_set_debug_buffer(void*);
+void attn5_set_debug_buffer(void*);
 int simt_gemm(const void*, const void*, void*, const void*, int, int, int, int, int,
               const long long*, const long long*, const long long*, float, int, int, cudaStream_t);
 int attn_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
@@ -30,6 +31,8 @@ int attn2_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, in
 int attn3_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
                       long long, long long, long long, float, int, cudaStream_t);
 int attn4_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
+                      long long, long long, long long, float, int, cudaStream_t);
+int attn5_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
                       long long, long long, long long, float, int, cudaStream_t);
 int patch_embed_tcgen05(const void*, int, const void*, long long, const float*, void*, int, int,
                         int, int, int, int, cudaStream_t);
@@ -68,6 +71,7 @@ void vt_debug_set_attn_buffer(void* ptr) {
   vt::attn2_set_debug_buffer(ptr);
   vt::attn3_set_debug_buffer(ptr);
   vt::attn4_set_debug_buffer(ptr);
+  vt::attn5_set_debug_buffer(ptr);
 }
 
 const char* vt_status_string(int status) {
@@ -138,15 +142,19 @@ int vt_gemm_strided(const void* A, const void* B, void* C, const void* bias, int
 int vt_flash_attn(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H,
                   int32_t N, int32_t dh, int64_t qkv_row_stride, int64_t qkv_batch_stride,
                   int64_t out_row_stride, int64_t out_batch_stride, float scale, void* stream) {
-  // persistent kernels: attn4 (double-buffered scores, four threads per row; head dim 64 and one KV
-  // block, i.e. N <= 208: default there; VT_ATTN4_MULTIBLOCK=1 forces it for longer sequences),
-  // attn3 (two slots x two column halves; head dim 80 and VT_ATTN_IMPL=3), attn2 (VT_ATTN_IMPL=2);
-  // VT_ATTN_IMPL=1 selects the one-tile-per-CTA kernel.  The alternatives exist for A/B measurements.
+  // Persistent kernels.  Head dim 64 and one KV block (N <= 208): attn5 (two de-phased softmax groups
+  // over double-buffered scores, default) or attn4 (one group of 16 warps, VT_ATTN_IMPL=4; also the
+  // online-softmax multi-block path with VT_ATTN4_MULTIBLOCK=1).  Everything else (longer sequences,
+  // head dim 80): attn3 (two slots x two column halves).  VT_ATTN_IMPL=3 / 2 / 1 force attn3 / attn2 /
+  // the one-tile-per-CTA kernel.  The alternatives exist for A/B measurements.
   static const int impl = [] {
     const char* e = getenv("VT_ATTN_IMPL");
-    return (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 4;
+    return (e && e[0] >= '1' && e[0] <= '4') ? (e[0] - '0') : 5;
   }();
-  if (impl == 4 && dh == 64 && (N <= 208 || getenv("VT_ATTN4_MULTIBLOCK")))
+  if (impl == 5 && dh == 64 && N <= 208)
+    return vt::attn5_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
+                                 out_row_stride, out_batch_stride, scale, next_direction(), S(stream));
+  if (impl >= 4 && dh == 64 && (N <= 208 || getenv("VT_ATTN4_MULTIBLOCK")))
     return vt::attn4_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
                                  out_row_stride, out_batch_stride, scale, next_direction(), S(stream));
   if (impl >= 3)

@@ -1,0 +1,498 @@
+// K3 (main variant for head dim 64, single KV block): persistent fused attention forward on
+// tcgen05 with TWO de-phased softmax groups over a double-buffered score tile.
+//
+//   ctx[b, i, h*64:(h+1)*64] = softmax_j( scale * q[b,i,h] . k[b,j,h] ) @ v[b,j,h]      (bf16, N <= 208)
+//
+// Replaces the reference's per-head matmul3 -> softmax -> matmul3 -> slice-assign chain
+// (vit/vit.py:60-72,101-108) for all heads at once; the score matrix never leaves the SM.
+//
+// What the earlier variants taught (profiles/README.md): the exponentials need ~1750 cycles of MUFU
+// per 128 x 208 tile and SM sub-partition, but a tile costs ~3800 cycles when the same warps walk
+// "row max -> exchange -> exp -> P ready -> (MMA round trip) -> read O -> store" in lock-step
+// (attn4), and ~3900 when two slots alias S, P and O in TMEM and so serialise their MMAs (attn3).
+// Here the two groups run the SAME lean per-item code as attn4 but on alternate items, half a period
+// apart, each on its own score buffer; all non-MUFU phases and the tensor-core round trips of one
+// group (wait for O, read + store it, wait for the next scores, row max) fall into the other
+// group's exp pass:
+//
+//   TMEM (512 columns)   S0 [0, 208)   S1 [208, 416)   O [416, 480)   row sums [480, 496)
+//   item v uses S[v & 1] and belongs to group v & 1; P (bf16x2) overwrites the thread's own consumed
+//   scores; O and the row sums (second N = 16 MMA against a tile of ones) are shared by both groups:
+//   PV_v is issued only after group (v-1) & 1 has read O_{v-1}, half a period earlier.
+//
+//   warps 0-7 / 8-15  softmax group 0 / 1: warp = 8 * group + 4 * column_half + row_quarter
+//   warp 16           TMA producer (decodes the items into a shared-memory ring, allocates TMEM)
+//   warp 17           MMA issuer: per item v: wait P_v, V_v, O_{v-1} read | PV_v (+ row sums) |
+//                     S_{v+2} = Q K^T into S[v & 1]
+//
+// Sequences longer than 208 keys and head dim 80 stay on attn3_sm100.cu.
+#include "attn_softmax.cuh"
+#include "common.cuh"
+#include "tensormap.h"
+
+namespace vt {
+
+namespace {
+
+constexpr int kDH5 = 64;
+constexpr int kQTile5 = 128;
+constexpr int kThreads5 = (16 + 2) * 32;               // 576
+constexpr int kQBytes5 = kQTile5 * kDH5 * 2;           // 16 KB
+constexpr int kMaxN5 = 208;
+constexpr int kSCols5 = 208;                           // columns per score buffer
+constexpr int kOCol5 = 2 * kSCols5;                    // 416: O (64 columns) then the row sums (16 columns)
+constexpr int kLCol5 = kOCol5 + kDH5;                  // 480
+constexpr int kStageBytes5 = 32 * 32 * 2;              // per warp: 32 rows x 32 bf16 (SWIZZLE_64B)
+constexpr int kOnesBytes5 = 16 * 16 * 2;
+constexpr int kRing5 = 8;
+constexpr int kSmemLimit5 = 232448;
+
+struct Attn5Params {
+  int N, H, B;
+  int nqt;            // query tiles per (image, head)
+  int bkv;            // key rows loaded per item (N rounded up to 16)
+  long long total_items;
+  int reverse;        // walk the images from the last to the first (L2 reuse, see api.cu)
+  float scale_log2;
+  long long* dbg;     // cycle counters, developer build only (make EXTRA=-DVT_ATTN5_DBG, tools/attn_dbg.py)
+};
+
+enum { C_QFULL = 0, C_QEMPTY = 2, C_KFULL = 4, C_KEMPTY = 6, C_VFULL = 8, C_VEMPTY = 10, C_SFULL = 12,
+       C_PFULL = 14, C_OFULL = 16, C_OREAD = 18, C_NBARS = 19 };
+
+__device__ __noinline__ void mbar_wait_slow5(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void mbar_wait_lean5(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow5(bar, parity);
+}
+
+// Row max over NG (1..7) groups of 16 score columns starting at TMEM address a.  Only the first nv
+// of the 16 * NG columns are real keys; nj - N < 16, so at most the LAST group is partly masked.
+// Groups are loaded in pairs, the next pair is in flight while the current one is folded.  (One
+// 64-column load + the rest was measured much slower: 94 vs 76 us per launch at C2.)
+template <int NG>
+__device__ __forceinline__ float max_groups5(uint32_t a, int nv) {
+  constexpr int kPairs = (NG + 1) / 2;
+  float m0 = -INFINITY, m1 = -INFINITY;
+  uint32_t r[kPairs][2][16];
+  auto load_pair = [&](int pr) {
+    tmem_ld_32x16(a + 32 * pr, r[pr][0]);
+    if (2 * pr + 1 < NG) tmem_ld_32x16(a + 32 * pr + 16, r[pr][1]);
+  };
+  load_pair(0);
+#pragma unroll
+  for (int pr = 0; pr < kPairs; ++pr) {
+    tmem_ld_wait();
+    if (pr + 1 < kPairs) load_pair(pr + 1);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int g = 2 * pr + h;
+      if (g < NG) {
+        if (g < NG - 1 || nv >= 16 * NG) {     // warp-uniform
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            m0 = fmax3(m0, __uint_as_float(r[pr][h][i]), __uint_as_float(r[pr][h][i + 1]));
+            m1 = fmax3(m1, __uint_as_float(r[pr][h][i + 2]), __uint_as_float(r[pr][h][i + 3]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (16 * g + i < nv) m0 = fmaxf(m0, __uint_as_float(r[pr][h][i]));
+        }
+      }
+    }
+  }
+  return fmaxf(m0, m1);
+}
+
+// one group: p = exp2(s * scale - m) -> bf16x2 -> TMEM columns dst .. dst + 7
+template <bool MASKED>
+__device__ __forceinline__ void exp_group5(const uint32_t (&r)[16], uint32_t dst, int nv_in_group, float scale_log2,
+                                           float m) {
+  uint32_t pk[8];
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), scale_log2, -m));
+    float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m));
+    if (MASKED) {
+      if (i >= nv_in_group) p0 = 0.f;
+      if (i + 1 >= nv_in_group) p1 = 0.f;
+    }
+    pk[i >> 1] = pack_bf16x2(p0, p1);
+  }
+  tmem_st_32x8(dst, pk);
+}
+
+// p = exp2(s * scale - m) over the same NG groups; P (bf16x2) of group g overwrites TMEM columns
+// a + 8g .. a + 8g + 7 (scores this thread has already consumed).  Groups are loaded in pairs, the
+// next pair is in flight during the math of the current one.
+template <int NG>
+__device__ __forceinline__ void exp_groups5(uint32_t a, int nv, float scale_log2, float m) {
+  constexpr int kPairs = (NG + 1) / 2;
+  uint32_t r[kPairs][2][16];
+  auto load_pair = [&](int pr) {
+    tmem_ld_32x16(a + 32 * pr, r[pr][0]);
+    if (2 * pr + 1 < NG) tmem_ld_32x16(a + 32 * pr + 16, r[pr][1]);
+  };
+  load_pair(0);
+#pragma unroll
+  for (int pr = 0; pr < kPairs; ++pr) {
+    tmem_ld_wait();
+    if (pr + 1 < kPairs) load_pair(pr + 1);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int g = 2 * pr + h;
+      if (g < NG) {
+        if (g < NG - 1 || nv >= 16 * NG)
+          exp_group5<false>(r[pr][h], a + 8 * g, 16, scale_log2, m);
+        else
+          exp_group5<true>(r[pr][h], a + 8 * g, nv - 16 * (NG - 1), scale_log2, m);
+      }
+    }
+  }
+  tmem_st_wait();
+}
+
+__global__ void __launch_bounds__(kThreads5, 1)
+attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                 const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_o,
+                 const Attn5Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int kv_bytes = p.bkv * kDH5 * 2;
+  // [Q0][Q1][K0][K1][V0][V1][staging 16 x 2 KB][ones][barriers][tmem slot][item ring][row max exchange]
+  const uint32_t q_smem = smem_base;
+  const uint32_t k_smem = q_smem + 2 * kQBytes5;
+  const uint32_t v_smem = k_smem + 2 * kv_bytes;
+  const int stage_off = 2 * kQBytes5 + 4 * kv_bytes;
+  const uint32_t stage_smem = smem_base + stage_off;
+  const int ones_off = stage_off + 16 * kStageBytes5;
+  const uint32_t ones_smem = smem_base + ones_off;
+  const int bar_off = ones_off + kOnesBytes5;
+  const uint32_t bar_base = smem_base + bar_off;
+  const uint32_t tmem_slot = bar_base + 8u * C_NBARS;
+  const int slot_off = bar_off + 8 * C_NBARS;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + slot_off);
+  int4* ring = reinterpret_cast<int4*>(smem_gen + slot_off + 8);                 // [kRing5] (16-byte aligned)
+  float* xm = reinterpret_cast<float*>(smem_gen + slot_off + 8 + 16 * kRing5);   // [2 groups][2 halves][128]
+  auto bar = [&](int i) { return bar_base + 8u * i; };
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp_idx == 17 && lane == 0) {
+    for (int i = 0; i < C_NBARS; ++i)
+      mbar_init(bar(i), (i == C_PFULL || i == C_PFULL + 1 || i == C_OREAD) ? 8 : 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_k);
+    tma_prefetch_desc(&tma_v);
+    tma_prefetch_desc(&tma_o);
+  }
+  if (warp_idx == 0) {   // the tile of ones behind the row-sum MMAs (read through the async proxy)
+    reinterpret_cast<uint4*>(smem_gen + ones_off)[lane] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
+  }
+  if (warp_idx == 16) {
+    tmem_alloc<512>(tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  // Work list of this CTA: items blockIdx.x, blockIdx.x + grid, ...
+  const long long first_item = blockIdx.x;
+  const long long item_step = gridDim.x;
+  const int n_items = (p.total_items > first_item)
+                          ? static_cast<int>((p.total_items - first_item + item_step - 1) / item_step)
+                          : 0;
+  const int nj = (p.N + 15) & ~15;     // score columns (MMA N)
+  const int n16 = nj >> 4;             // 16-column groups: half 0 takes the first (n16 + 1) / 2
+  const int ng0 = (n16 + 1) >> 1;
+
+  if (warp_idx == 16) {
+    // ------------------------------------------------------------------ TMA producer
+    for (int it = 0; it < n_items; ++it) {
+      const unsigned item = static_cast<unsigned>(first_item + static_cast<long long>(it) * item_step);
+      const int qt = static_cast<int>(item % static_cast<unsigned>(p.nqt));   // total_items < 2^31 (host)
+      const unsigned bh = item / static_cast<unsigned>(p.nqt);
+      const int head = static_cast<int>(bh % static_cast<unsigned>(p.H));
+      int img = static_cast<int>(bh / static_cast<unsigned>(p.H));
+      if (p.reverse) img = p.B - 1 - img;
+      const int b = it & 1;
+      const uint32_t ph = (static_cast<uint32_t>(it) >> 1) & 1u;
+      mbar_wait(bar(C_QEMPTY + b), ph ^ 1u);
+      if (elect_one_sync()) {
+        // item coordinates for the softmax warps: visible to them through the barrier chain
+        // C_QFULL -> (MMA issuer) -> C_SFULL; the ring is deeper than the producer can run ahead
+        ring[it & (kRing5 - 1)] = make_int4(img, head, qt, 0);
+        mbar_arrive_expect_tx(bar(C_QFULL + b), kQBytes5);
+        tma_load_3d(&tma_q, bar(C_QFULL + b), q_smem + b * kQBytes5, head * kDH5, qt * kQTile5, img, kEvictFirst);
+      }
+      __syncwarp();
+      mbar_wait(bar(C_KEMPTY + b), ph ^ 1u);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(bar(C_KFULL + b), kv_bytes);
+        tma_load_3d(&tma_k, bar(C_KFULL + b), k_smem + b * kv_bytes, head * kDH5, 0, img, kEvictNormal);
+      }
+      __syncwarp();
+      mbar_wait(bar(C_VEMPTY + b), ph ^ 1u);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(bar(C_VFULL + b), kv_bytes);
+        tma_load_3d(&tma_v, bar(C_VFULL + b), v_smem + b * kv_bytes, head * kDH5, 0, img, kEvictNormal);
+      }
+      __syncwarp();
+    }
+  } else if (warp_idx == 17) {
+    // ------------------------------------------------------------------ MMA issuer
+    // S_v = Q K^T into score buffer v & 1 (free: PV_{v-2}, issued earlier by this thread, is the last
+    // reader of that buffer and tcgen05.mma executes in issue order).
+    auto issue_scores = [&](int v) {
+      const int b = v & 1;
+      const uint32_t ph = (static_cast<uint32_t>(v) >> 1) & 1u;
+      mbar_wait(bar(C_QFULL + b), ph);
+      mbar_wait(bar(C_KFULL + b), ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t idesc = make_idesc_bf16(kQTile5, nj, 0, 0);
+        const uint64_t qd = make_desc_kmajor_sw128(q_smem + b * kQBytes5);
+        const uint64_t kd = make_desc_kmajor_sw128(k_smem + b * kv_bytes);
+#pragma unroll
+        for (int k = 0; k < kDH5 / 16; ++k)
+          umma_ss(tmem_base + b * kSCols5, qd + 2 * k, kd + 2 * k, idesc, k != 0 ? 1u : 0u);
+        umma_commit(bar(C_SFULL + b));
+        umma_commit(bar(C_KEMPTY + b));
+        umma_commit(bar(C_QEMPTY + b));
+      }
+      __syncwarp();
+    };
+    if (n_items > 0) issue_scores(0);
+    if (n_items > 1) issue_scores(1);
+    for (int v = 0; v < n_items; ++v) {
+      const int b = v & 1;
+      const uint32_t ph = (static_cast<uint32_t>(v) >> 1) & 1u;
+      // ---- O_v = P_v V_v and the row sums P_v 1
+      mbar_wait(bar(C_VFULL + b), ph);
+      if (v > 0) mbar_wait(bar(C_OREAD), static_cast<uint32_t>(v - 1) & 1u);   // O columns free
+      mbar_wait(bar(C_PFULL + b), ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t idesc = make_idesc_bf16(kQTile5, kDH5, 0, 1);
+        const uint32_t idesc_l = make_idesc_bf16(kQTile5, 16, 0, 1);
+        const uint64_t vd = make_desc_mnmajor_sw128(v_smem + b * kv_bytes, 1024);
+        const uint64_t od = make_smem_desc(ones_smem, 256, 256, 6);   // every element is 1: layout is moot
+        const uint32_t s_tmem = tmem_base + b * kSCols5;
+        for (int k = 0; k < n16; ++k) {   // 16 keys: 8 packed P columns, 2048 B of V
+          // P of group k lives at the start of its owner's columns: half 0 owns groups [0, ng0)
+          const uint32_t a_tmem = s_tmem + (k < ng0 ? 8 * k : 16 * ng0 + 8 * (k - ng0));
+          umma_ts(tmem_base + kOCol5, a_tmem, vd + 128 * k, idesc, k != 0 ? 1u : 0u);
+          umma_ts(tmem_base + kLCol5, a_tmem, od, idesc_l, k != 0 ? 1u : 0u);
+        }
+        umma_commit(bar(C_OFULL + b));
+        umma_commit(bar(C_VEMPTY + b));
+      }
+      __syncwarp();
+      if (v + 2 < n_items) issue_scores(v + 2);
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warps
+    const int g = warp_idx >> 3;             // group = score buffer = item parity
+    const int half = (warp_idx >> 2) & 1;    // column half
+    const int rq = warp_idx & 3;             // row quarter = TMEM lane group
+    const int row_in_tile = rq * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(rq * 32) << 16);
+    const uint32_t stage_addr = stage_smem + warp_idx * kStageBytes5;
+    uint8_t* stage_row = smem_gen + stage_off + warp_idx * kStageBytes5 + lane * 64;
+    const int sw = (lane >> 1) & 3;          // SWIZZLE_64B phase of this thread's staging row
+    const int bar_id = 1 + g * 4 + rq;       // named barrier of the two warps sharing these rows
+    float* x_mine = xm + (g * 2 + half) * kQTile5 + row_in_tile;
+    const float* x_other = xm + (g * 2 + (half ^ 1)) * kQTile5 + row_in_tile;
+    // my columns: 16-column groups [g0, g0 + ng)
+    const int ng = half ? (n16 - ng0) : ng0;
+    const int c0 = half ? 16 * ng0 : 0;
+    const int nvr = p.N - c0;                // valid columns counted from my first
+    const uint32_t t_mine = t_lane + g * kSCols5 + c0;
+
+#ifdef VT_ATTN5_DBG
+    const bool dbg_on = p.dbg != nullptr;
+    unsigned dacc[7] = {0, 0, 0, 0, 0, 0, 0};
+    const unsigned dt0 = static_cast<unsigned>(clock());
+    unsigned tc = 0;
+#define VT_TICK5(i) if (dbg_on) { const unsigned t_ = static_cast<unsigned>(clock()); dacc[i] += t_ - tc; tc = t_; }
+#define VT_TICK5_START() if (dbg_on) tc = static_cast<unsigned>(clock());
+#else
+#define VT_TICK5(i)
+#define VT_TICK5_START()
+#endif
+    uint32_t ph = 0;
+    for (int v = g; v < n_items; v += 2, ph ^= 1u) {
+      VT_TICK5_START()
+      mbar_wait_lean5(bar(C_SFULL + g), ph);
+      VT_TICK5(0)
+      tc_fence_after();
+      const int4 desc = ring[v & (kRing5 - 1)];   // (image, head, query tile)
+      // warp-uniform: all 32 query rows of this warp lie beyond the sequence (N = 197: the last row
+      // quarter of every second tile).  Such a warp keeps the barrier protocol and skips the work;
+      // its P rows stay undefined (MMA rows are independent, the rows are never stored).
+      const bool live = desc.z * kQTile5 + rq * 32 < p.N;
+      if (live) {
+        // pass 1: row max over my columns, exchanged with the other half of the row
+        float mx = -INFINITY;
+        switch (ng) {   // warp-uniform
+          case 7: mx = max_groups5<7>(t_mine, nvr); break;
+          case 6: mx = max_groups5<6>(t_mine, nvr); break;
+          case 5: mx = max_groups5<5>(t_mine, nvr); break;
+          case 4: mx = max_groups5<4>(t_mine, nvr); break;
+          case 3: mx = max_groups5<3>(t_mine, nvr); break;
+          case 2: mx = max_groups5<2>(t_mine, nvr); break;
+          case 1: mx = max_groups5<1>(t_mine, nvr); break;
+          default: break;
+        }
+        *x_mine = mx;
+        VT_TICK5(1)
+        named_bar_sync(bar_id, 64);
+        const float m = fmaxf(mx, *x_other) * p.scale_log2;
+        VT_TICK5(2)
+        // pass 2: exponentials; P overwrites my own consumed scores
+        switch (ng) {
+          case 7: exp_groups5<7>(t_mine, nvr, p.scale_log2, m); break;
+          case 6: exp_groups5<6>(t_mine, nvr, p.scale_log2, m); break;
+          case 5: exp_groups5<5>(t_mine, nvr, p.scale_log2, m); break;
+          case 4: exp_groups5<4>(t_mine, nvr, p.scale_log2, m); break;
+          case 3: exp_groups5<3>(t_mine, nvr, p.scale_log2, m); break;
+          case 2: exp_groups5<2>(t_mine, nvr, p.scale_log2, m); break;
+          case 1: exp_groups5<1>(t_mine, nvr, p.scale_log2, m); break;
+          default: break;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(C_PFULL + g));
+      VT_TICK5(3)
+
+      // the previous store out of my staging tile has long been read: check now, off the critical path
+      if (lane == 0) tma_store_wait_read<0>();
+      // O_v: my 32 output columns and the row sum
+      mbar_wait_lean5(bar(C_OFULL + g), ph);
+      VT_TICK5(4)
+      tc_fence_after();
+      uint32_t r[32];
+      uint32_t rl[8];
+      if (live) {
+        tmem_ld_32x32(t_lane + kOCol5 + half * 32, r);
+        tmem_ld_32x8(t_lane + kLCol5, rl);   // every one of the 16 sum columns holds the row sum
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(C_OREAD));
+      VT_TICK5(5)
+      if (!live) continue;
+      float inv;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(__uint_as_float(rl[0])));
+      // stage this warp's [32 rows x 32 columns] as a SWIZZLE_64B tile and TMA-store it (the staging
+      // tile is free: lane 0 waited for the previous store above, the __syncwarp after the O read
+      // ordered that before every lane's writes)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        uint4 o4;
+        o4.x = pack_bf16x2(__uint_as_float(r[8 * jj + 0]) * inv, __uint_as_float(r[8 * jj + 1]) * inv);
+        o4.y = pack_bf16x2(__uint_as_float(r[8 * jj + 2]) * inv, __uint_as_float(r[8 * jj + 3]) * inv);
+        o4.z = pack_bf16x2(__uint_as_float(r[8 * jj + 4]) * inv, __uint_as_float(r[8 * jj + 5]) * inv);
+        o4.w = pack_bf16x2(__uint_as_float(r[8 * jj + 6]) * inv, __uint_as_float(r[8 * jj + 7]) * inv);
+        *reinterpret_cast<uint4*>(stage_row + ((jj ^ sw) << 4)) = o4;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                     :
+                     : "l"(reinterpret_cast<uint64_t>(&tma_o)), "r"(stage_addr),
+                       "r"(desc.y * kDH5 + half * 32), "r"(desc.z * kQTile5 + rq * 32), "r"(desc.x)
+                     : "memory");
+        tma_store_commit();
+      }
+      VT_TICK5(6)
+    }
+    if (lane == 0) tma_store_wait<0>();
+#ifdef VT_ATTN5_DBG
+    if (dbg_on && (warp_idx & 7) == 0 && lane == 0) {
+      long long* d = p.dbg + (2LL * blockIdx.x + g) * 8;
+      for (int i = 0; i < 7; ++i) d[i] = dacc[i];
+      d[7] = static_cast<unsigned>(clock()) - dt0;
+    }
+#endif
+#undef VT_TICK5
+#undef VT_TICK5_START
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 16) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+long long* g_attn5_dbg = nullptr;
+
+}  // namespace
+
+void attn5_set_debug_buffer(void* ptr) { g_attn5_dbg = static_cast<long long*>(ptr); }
+
+int attn5_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, int B, int H, int N,
+                      int dh, long long qkv_row_stride, long long qkv_batch_stride,
+                      long long out_row_stride, long long out_batch_stride, float scale, int reverse,
+                      cudaStream_t stream) {
+  if (!q || !k || !v || !out || B <= 0 || H <= 0 || N <= 0) return VT_ERR_ARG;
+  if (dh != kDH5 || N > kMaxN5) return VT_ERR_UNSUPPORTED;
+  if ((qkv_row_stride % 8) || (qkv_batch_stride % 8) || (out_row_stride % 8) || (out_batch_stride % 8))
+    return VT_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+       reinterpret_cast<uintptr_t>(out)) & 15)
+    return VT_ERR_ALIGN;
+
+  Attn5Params p;
+  p.N = N;
+  p.H = H;
+  p.B = B;
+  p.nqt = (N + kQTile5 - 1) / kQTile5;
+  p.bkv = (N + 15) & ~15;
+  p.total_items = static_cast<long long>(B) * H * p.nqt;
+  if (p.total_items >= (1LL << 31)) return VT_ERR_UNSUPPORTED;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.reverse = reverse;
+  p.dbg = g_attn5_dbg;
+  const int smem = 1024 + 2 * kQBytes5 + 4 * p.bkv * kDH5 * 2 + 16 * kStageBytes5 + kOnesBytes5 + 8 * C_NBARS + 8 +
+                   16 * kRing5 + 2 * 2 * kQTile5 * 4;
+  if (smem > kSmemLimit5) return VT_ERR_UNSUPPORTED;
+
+  const uint64_t cols = static_cast<uint64_t>(H) * dh;
+  CUtensorMap tq, tk, tv, to;
+  int rc = make_tmap_bf16_3d(&tq, q, cols, N, B, qkv_row_stride, qkv_batch_stride, kDH5, kQTile5, TMAP_SW_128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tk, k, cols, N, B, qkv_row_stride, qkv_batch_stride, kDH5, p.bkv, TMAP_SW_128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tv, v, cols, N, B, qkv_row_stride, qkv_batch_stride, kDH5, p.bkv, TMAP_SW_128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&to, out, cols, N, B, out_row_stride, out_batch_stride, 32, 32, TMAP_SW_64);
+  if (rc) return rc;
+
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn5_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    smem_set = smem;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long grid = p.total_items < sms ? p.total_items : sms;
+  attn5_fwd_kernel<<<static_cast<unsigned>(grid), kThreads5, smem, stream>>>(tq, tk, tv, to, p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace vt
