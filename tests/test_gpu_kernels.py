@@ -239,6 +239,19 @@ def test_flash_attention_double_buffered_kernel(B, H, N, gain, monkeypatch):
     assert torch.equal(sub, got[:1])
 
 
+@pytest.mark.parametrize("impl", ["1", "2", "3", "4"])
+@pytest.mark.parametrize("B,H,N", [(3, 5, 197), (1, 2, 130), (2, 2, 64)])
+def test_flash_attention_kernel_generations(impl, B, H, N, monkeypatch):
+    """The earlier attention kernels stay in the library as A/B variants (VT_ATTN_IMPL) and attn3 is the
+    production path for long sequences / head dim 80: all of them must agree with the reference."""
+    from vit.kernels import flash_attention
+    monkeypatch.setenv("VT_ATTN_IMPL", impl)
+    qkv = torch.randn(B, N, 3 * H * 64, device=dev()).bfloat16()
+    got = flash_attention(qkv, H)
+    assert torch.isfinite(got.float()).all()
+    assert rel_err(got, _attn_ref(qkv, H)) <= 1e-2
+
+
 def test_flash_attention_peaky_scores():
     """Large logits: the online max subtraction must keep exp() in range."""
     from vit.kernels import flash_attention

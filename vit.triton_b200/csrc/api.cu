@@ -147,10 +147,9 @@ int vt_flash_attn(const void* q, const void* k, const void* v, void* out, int32_
   // online-softmax multi-block path with VT_ATTN4_MULTIBLOCK=1).  Everything else (longer sequences,
   // head dim 80): attn3 (two slots x two column halves).  VT_ATTN_IMPL=3 / 2 / 1 force attn3 / attn2 /
   // the one-tile-per-CTA kernel.  The alternatives exist for A/B measurements.
-  static const int impl = [] {
-    const char* e = getenv("VT_ATTN_IMPL");
-    return (e && e[0] >= '1' && e[0] <= '4') ? (e[0] - '0') : 5;
-  }();
+  // (read on every call — a getenv is nothing next to a launch — so tests can exercise every variant)
+  const char* e = getenv("VT_ATTN_IMPL");
+  const int impl = (e && e[0] >= '1' && e[0] <= '4') ? (e[0] - '0') : 5;
   if (impl == 5 && dh == 64 && N <= 208)
     return vt::attn5_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
                                  out_row_stride, out_batch_stride, scale, next_direction(), S(stream));
