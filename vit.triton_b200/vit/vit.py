@@ -2,7 +2,8 @@
 
 Class names, constructor arguments, parameter names / shapes (hence state-dict keys) and forward
 signatures are those of cmeraki/vit.triton so this file drops in for the reference's; what runs
-underneath is different.  Each ``Transformer`` block executes as SEVEN launches of hand-written
+underneath is different.  Each ``Transformer`` block executes as SEVEN launches (six with the default
+LayerNorm fold: ``layernorm_before`` of blocks 1.. runs inside the QKV GEMM's epilogue) of hand-written
 sm_100a kernels over the flattened (B*N, D) activation:
 
     LN1 -> QKV GEMM (all heads, one launch) -> fused attention -> out-proj GEMM (+bias +residual)
