@@ -239,6 +239,22 @@ def test_flash_attention_double_buffered_kernel(B, H, N, gain, monkeypatch):
     assert torch.equal(sub, got[:1])
 
 
+@pytest.mark.parametrize("B,H,N,gain", [(2, 3, 577, 1.0), (1, 2, 209, 1.0), (3, 2, 416, 1.0), (1, 2, 577, 8.0),
+                                        (1, 1, 417, 1.0), (5, 7, 257, 1.0), (148, 2, 209, 1.0), (1, 1, 1000, 1.0)])
+def test_flash_attention_two_group_kernel_multiblock(B, H, N, gain):
+    """attn5mb (default for head dim 64, N > 208): the two-group kernel on sequences of several KV
+    blocks (online softmax).  Item counts
+    per CTA that are odd, one, or zero for the second group are all covered by the shapes."""
+    from vit.kernels import flash_attention
+    qkv = (gain * torch.randn(B, N, 3 * H * 64, device=dev())).bfloat16()
+    got = flash_attention(qkv, H)
+    want = _attn_ref(qkv, H)
+    assert torch.isfinite(got.float()).all()
+    assert rel_err(got, want) <= (1e-2 if gain == 1.0 else 2e-2)
+    sub = flash_attention(qkv[:1].contiguous(), H)
+    assert torch.equal(sub, got[:1])
+
+
 @pytest.mark.parametrize("impl", ["1", "2", "3", "4"])
 @pytest.mark.parametrize("B,H,N", [(3, 5, 197), (1, 2, 130), (2, 2, 64)])
 def test_flash_attention_kernel_generations(impl, B, H, N, monkeypatch):

@@ -34,6 +34,8 @@ int attn4_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, in
                       long long, long long, long long, float, int, cudaStream_t);
 int attn5_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
                       long long, long long, long long, float, int, cudaStream_t);
+int attn5mb_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
+                        long long, long long, long long, float, int, cudaStream_t);
 int patch_embed_tcgen05(const void*, int, const void*, long long, const float*, void*, int, int,
                         int, int, int, int, cudaStream_t);
 int patching(const void*, void*, int, int, int, int, int, int, cudaStream_t);
@@ -142,10 +144,10 @@ int vt_gemm_strided(const void* A, const void* B, void* C, const void* bias, int
 int vt_flash_attn(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H,
                   int32_t N, int32_t dh, int64_t qkv_row_stride, int64_t qkv_batch_stride,
                   int64_t out_row_stride, int64_t out_batch_stride, float scale, void* stream) {
-  // Persistent kernels.  Head dim 64 and one KV block (N <= 208): attn5 (two de-phased softmax groups
-  // over double-buffered scores, default) or attn4 (one group of 16 warps, VT_ATTN_IMPL=4; also the
-  // online-softmax multi-block path with VT_ATTN4_MULTIBLOCK=1).  Everything else (longer sequences,
-  // head dim 80): attn3 (two slots x two column halves).  VT_ATTN_IMPL=3 / 2 / 1 force attn3 / attn2 /
+  // Persistent kernels.  Head dim 64: attn5 (two de-phased softmax groups over double-buffered scores;
+  // one KV block for N <= 208, the online-softmax multi-block kernel beyond), default.  attn4 (one
+  // group of 16 warps) with VT_ATTN_IMPL=4 (N <= 208, or any N with VT_ATTN4_MULTIBLOCK=1).  Head
+  // dim 80: attn3 (two slots x two column halves).  VT_ATTN_IMPL=3 / 2 / 1 force attn3 / attn2 /
   // the one-tile-per-CTA kernel.  The alternatives exist for A/B measurements.
   // (read on every call — a getenv is nothing next to a launch — so tests can exercise every variant)
   const char* e = getenv("VT_ATTN_IMPL");
@@ -153,6 +155,11 @@ int vt_flash_attn(const void* q, const void* k, const void* v, void* out, int32_
   if (impl == 5 && dh == 64 && N <= 208)
     return vt::attn5_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
                                  out_row_stride, out_batch_stride, scale, next_direction(), S(stream));
+  if (impl == 5 && dh == 64) {   // N > 208: several KV blocks per item, same two-group structure
+    const int rc = vt::attn5mb_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
+                                           out_row_stride, out_batch_stride, scale, next_direction(), S(stream));
+    if (rc != VT_ERR_UNSUPPORTED) return rc;
+  }
   if (impl >= 4 && dh == 64 && (N <= 208 || getenv("VT_ATTN4_MULTIBLOCK")))
     return vt::attn4_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
                                  out_row_stride, out_batch_stride, scale, next_direction(), S(stream));

@@ -437,6 +437,381 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Multi-block variant (N > 208: ViT-B/16 @ 384 has 577 tokens = 3 KV blocks of 208/208/161): the same
+// two de-phased groups, group g owns the items of parity g and walks ALL KV blocks of an item on its
+// own score buffer with the online-softmax recurrence (running max, rescale factor alpha, output
+// accumulator of 32 columns per thread in registers).  A "unit" is one KV block of one item; the
+// MMA issuer and the producer alternate between the two groups' unit streams.
+// ------------------------------------------------------------------------------------------------
+struct Attn5MbParams {
+  int N, H, B;
+  int nqt;
+  int bkv, nblk;      // key rows per block (multiple of 16, <= 208), blocks per item (>= 2)
+  long long total_items;
+  int reverse;
+  float scale_log2;
+};
+
+// Non-pipelined forms for the multi-block kernel: the 33 accumulator registers that stay live
+// across the passes leave room for one pair of groups (32 registers) in flight, not two.
+template <int NG>
+__device__ __forceinline__ float max_groups5_np(uint32_t a, int nv) {
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int pr = 0; pr < (NG + 1) / 2; ++pr) {
+    uint32_t r[2][16];
+    tmem_ld_32x16(a + 32 * pr, r[0]);
+    if (2 * pr + 1 < NG) tmem_ld_32x16(a + 32 * pr + 16, r[1]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int g = 2 * pr + h;
+      if (g < NG) {
+        if (g < NG - 1 || nv >= 16 * NG) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            m0 = fmax3(m0, __uint_as_float(r[h][i]), __uint_as_float(r[h][i + 1]));
+            m1 = fmax3(m1, __uint_as_float(r[h][i + 2]), __uint_as_float(r[h][i + 3]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (16 * g + i < nv) m0 = fmaxf(m0, __uint_as_float(r[h][i]));
+        }
+      }
+    }
+  }
+  return fmaxf(m0, m1);
+}
+
+template <int NG>
+__device__ __forceinline__ void exp_groups5_np(uint32_t a, int nv, float scale_log2, float m) {
+#pragma unroll
+  for (int pr = 0; pr < (NG + 1) / 2; ++pr) {
+    uint32_t r[2][16];
+    tmem_ld_32x16(a + 32 * pr, r[0]);
+    if (2 * pr + 1 < NG) tmem_ld_32x16(a + 32 * pr + 16, r[1]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int g = 2 * pr + h;
+      if (g < NG) {
+        if (g < NG - 1 || nv >= 16 * NG)
+          exp_group5<false>(r[h], a + 8 * g, 16, scale_log2, m);
+        else
+          exp_group5<true>(r[h], a + 8 * g, nv - 16 * (NG - 1), scale_log2, m);
+      }
+    }
+  }
+  tmem_st_wait();
+}
+
+__global__ void __launch_bounds__(kThreads5, 1)
+attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                   const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_o,
+                   const Attn5MbParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int kv_bytes = p.bkv * kDH5 * 2;
+  // same layout as attn5_fwd_kernel; buffers are indexed by GROUP
+  const uint32_t q_smem = smem_base;
+  const uint32_t k_smem = q_smem + 2 * kQBytes5;
+  const uint32_t v_smem = k_smem + 2 * kv_bytes;
+  const int stage_off = 2 * kQBytes5 + 4 * kv_bytes;
+  const uint32_t stage_smem = smem_base + stage_off;
+  const int ones_off = stage_off + 16 * kStageBytes5;
+  const uint32_t ones_smem = smem_base + ones_off;
+  const int bar_off = ones_off + kOnesBytes5;
+  const uint32_t bar_base = smem_base + bar_off;
+  const uint32_t tmem_slot = bar_base + 8u * C_NBARS;
+  const int slot_off = bar_off + 8 * C_NBARS;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + slot_off);
+  int4* ring = reinterpret_cast<int4*>(smem_gen + slot_off + 8);
+  float* xm = reinterpret_cast<float*>(smem_gen + slot_off + 8 + 16 * kRing5);
+  auto bar = [&](int i) { return bar_base + 8u * i; };
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp_idx == 17 && lane == 0) {
+    for (int i = 0; i < C_NBARS; ++i)
+      mbar_init(bar(i), (i == C_PFULL || i == C_PFULL + 1 || i == C_OREAD) ? 8 : 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_k);
+    tma_prefetch_desc(&tma_v);
+    tma_prefetch_desc(&tma_o);
+  }
+  if (warp_idx == 0) {
+    reinterpret_cast<uint4*>(smem_gen + ones_off)[lane] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
+  }
+  if (warp_idx == 16) {
+    tmem_alloc<512>(tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const long long first_item = blockIdx.x;
+  const long long item_step = gridDim.x;
+  const int n_items = (p.total_items > first_item)
+                          ? static_cast<int>((p.total_items - first_item + item_step - 1) / item_step)
+                          : 0;
+  const int nblk = p.nblk;
+  const int bkv = p.bkv;
+  // items of group g: g, g + 2, ...; its unit stream has n_items_g * nblk entries
+  const int units0 = ((n_items + 1) >> 1) * nblk;
+  const int units1 = (n_items >> 1) * nblk;
+  // the two block shapes: blocks 0 .. nblk-2 have bkv keys, the last one the rest
+  const int nv_last = p.N - (nblk - 1) * bkv;
+  const int nj_full = bkv;
+  const int nj_last = (nv_last + 15) & ~15;
+
+  if (warp_idx == 16) {
+    // ------------------------------------------------------------------ TMA producer
+    // pairs of items (one per group), their blocks interleaved so neither group waits for the other
+    for (int it0 = 0; it0 < n_items; it0 += 2) {
+      int img[2], head[2];
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int it = it0 + g;
+        if (it >= n_items) continue;
+        const unsigned item = static_cast<unsigned>(first_item + static_cast<long long>(it) * item_step);
+        const int qt = static_cast<int>(item % static_cast<unsigned>(p.nqt));
+        const unsigned bh = item / static_cast<unsigned>(p.nqt);
+        head[g] = static_cast<int>(bh % static_cast<unsigned>(p.H));
+        img[g] = static_cast<int>(bh / static_cast<unsigned>(p.H));
+        if (p.reverse) img[g] = p.B - 1 - img[g];
+        const uint32_t ph = (static_cast<uint32_t>(it0) >> 1) & 1u;   // group-local item index = it0 / 2
+        mbar_wait(bar(C_QEMPTY + g), ph ^ 1u);
+        if (elect_one_sync()) {
+          ring[it & (kRing5 - 1)] = make_int4(img[g], head[g], qt, 0);
+          mbar_arrive_expect_tx(bar(C_QFULL + g), kQBytes5);
+          tma_load_3d(&tma_q, bar(C_QFULL + g), q_smem + g * kQBytes5, head[g] * kDH5, qt * kQTile5, img[g], kEvictFirst);
+        }
+        __syncwarp();
+      }
+      for (int j = 0; j < nblk; ++j) {
+        const uint32_t ph = static_cast<uint32_t>((it0 >> 1) * nblk + j) & 1u;   // group-local unit index
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (it0 + g >= n_items) continue;
+          mbar_wait(bar(C_KEMPTY + g), ph ^ 1u);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(bar(C_KFULL + g), kv_bytes);
+            tma_load_3d(&tma_k, bar(C_KFULL + g), k_smem + g * kv_bytes, head[g] * kDH5, j * bkv, img[g], kEvictNormal);
+          }
+          __syncwarp();
+          mbar_wait(bar(C_VEMPTY + g), ph ^ 1u);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(bar(C_VFULL + g), kv_bytes);
+            tma_load_3d(&tma_v, bar(C_VFULL + g), v_smem + g * kv_bytes, head[g] * kDH5, j * bkv, img[g], kEvictNormal);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp_idx == 17) {
+    // ------------------------------------------------------------------ MMA issuer
+    // S of group g's unit lu into score buffer g (free: the PV of the group's previous unit, issued
+    // earlier by this thread, is the last reader and tcgen05.mma executes in issue order).
+    auto issue_scores = [&](int g, int lu) {
+      const int li = lu / nblk;            // group-local item index
+      const int j = lu - li * nblk;
+      const int nj = (j == nblk - 1) ? nj_last : nj_full;
+      if (j == 0) mbar_wait(bar(C_QFULL + g), static_cast<uint32_t>(li) & 1u);
+      mbar_wait(bar(C_KFULL + g), static_cast<uint32_t>(lu) & 1u);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t idesc = make_idesc_bf16(kQTile5, nj, 0, 0);
+        const uint64_t qd = make_desc_kmajor_sw128(q_smem + g * kQBytes5);
+        const uint64_t kd = make_desc_kmajor_sw128(k_smem + g * kv_bytes);
+#pragma unroll
+        for (int k = 0; k < kDH5 / 16; ++k)
+          umma_ss(tmem_base + g * kSCols5, qd + 2 * k, kd + 2 * k, idesc, k != 0 ? 1u : 0u);
+        umma_commit(bar(C_SFULL + g));
+        umma_commit(bar(C_KEMPTY + g));
+        if (j == nblk - 1) umma_commit(bar(C_QEMPTY + g));
+      }
+      __syncwarp();
+    };
+    int lu[2] = {0, 0};
+    const int units[2] = {units0, units1};
+    if (units0 > 0) issue_scores(0, 0);
+    if (units1 > 0) issue_scores(1, 0);
+    int issued = 0;
+    int g = 0;
+    while (lu[0] < units0 || lu[1] < units1) {
+      if (lu[g] >= units[g]) g ^= 1;
+      const int u = lu[g];
+      const uint32_t ph = static_cast<uint32_t>(u) & 1u;
+      const int j = u % nblk;
+      const int nj = (j == nblk - 1) ? nj_last : nj_full;
+      const int n16 = nj >> 4;
+      const int ng0 = (n16 + 1) >> 1;
+      mbar_wait(bar(C_VFULL + g), ph);
+      if (issued > 0) mbar_wait(bar(C_OREAD), static_cast<uint32_t>(issued - 1) & 1u);   // O columns free
+      mbar_wait(bar(C_PFULL + g), ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t idesc = make_idesc_bf16(kQTile5, kDH5, 0, 1);
+        const uint32_t idesc_l = make_idesc_bf16(kQTile5, 16, 0, 1);
+        const uint64_t vd = make_desc_mnmajor_sw128(v_smem + g * kv_bytes, 1024);
+        const uint64_t od = make_smem_desc(ones_smem, 256, 256, 6);
+        const uint32_t s_tmem = tmem_base + g * kSCols5;
+        for (int k = 0; k < n16; ++k) {
+          const uint32_t a_tmem = s_tmem + (k < ng0 ? 8 * k : 16 * ng0 + 8 * (k - ng0));
+          umma_ts(tmem_base + kOCol5, a_tmem, vd + 128 * k, idesc, k != 0 ? 1u : 0u);
+          umma_ts(tmem_base + kLCol5, a_tmem, od, idesc_l, k != 0 ? 1u : 0u);
+        }
+        umma_commit(bar(C_OFULL + g));
+        umma_commit(bar(C_VEMPTY + g));
+      }
+      __syncwarp();
+      ++issued;
+      if (++lu[g] < units[g]) issue_scores(g, lu[g]);
+      g ^= 1;
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warps
+    const int g = warp_idx >> 3;
+    const int half = (warp_idx >> 2) & 1;
+    const int rq = warp_idx & 3;
+    const int row_in_tile = rq * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(rq * 32) << 16);
+    const uint32_t stage_addr = stage_smem + warp_idx * kStageBytes5;
+    uint8_t* stage_row = smem_gen + stage_off + warp_idx * kStageBytes5 + lane * 64;
+    const int sw = (lane >> 1) & 3;
+    const int bar_id = 1 + g * 4 + rq;
+    float* x_mine = xm + (g * 2 + half) * kQTile5 + row_in_tile;
+    const float* x_other = xm + (g * 2 + (half ^ 1)) * kQTile5 + row_in_tile;
+    // my columns in the two block shapes
+    const int n16_full = nj_full >> 4, n16_last = nj_last >> 4;
+    const int ng0_full = (n16_full + 1) >> 1, ng0_last = (n16_last + 1) >> 1;
+    const int ng_full = half ? (n16_full - ng0_full) : ng0_full;
+    const int ng_last = half ? (n16_last - ng0_last) : ng0_last;
+    const int c0_full = half ? 16 * ng0_full : 0, c0_last = half ? 16 * ng0_last : 0;
+    const int units = g ? units1 : units0;
+
+    int4 desc = make_int4(0, 0, 0, 0);
+    bool live = false;
+    float m_run = -INFINITY, l_acc = 0.f;
+    float o_acc[32];
+    int j = 0, li = 0;
+    for (int lu = 0; lu < units; ++lu) {
+      const uint32_t ph = static_cast<uint32_t>(lu) & 1u;
+      const bool last_blk = (j == nblk - 1);
+      const int ng = last_blk ? ng_last : ng_full;
+      const int c0 = last_blk ? c0_last : c0_full;
+      const int nvr = (last_blk ? nv_last : nj_full) - c0;
+      const uint32_t t_mine = t_lane + g * kSCols5 + c0;
+
+      mbar_wait_lean5(bar(C_SFULL + g), ph);
+      tc_fence_after();
+      if (j == 0) {
+        desc = ring[(2 * li + g) & (kRing5 - 1)];
+        live = desc.z * kQTile5 + rq * 32 < p.N;
+        m_run = -INFINITY;
+      }
+      float alpha = 0.f;
+      if (live) {
+        float mx = -INFINITY;
+        switch (ng) {   // warp-uniform
+          case 7: mx = max_groups5_np<7>(t_mine, nvr); break;
+          case 6: mx = max_groups5_np<6>(t_mine, nvr); break;
+          case 5: mx = max_groups5_np<5>(t_mine, nvr); break;
+          case 4: mx = max_groups5_np<4>(t_mine, nvr); break;
+          case 3: mx = max_groups5_np<3>(t_mine, nvr); break;
+          case 2: mx = max_groups5_np<2>(t_mine, nvr); break;
+          case 1: mx = max_groups5_np<1>(t_mine, nvr); break;
+          default: break;
+        }
+        *x_mine = mx;
+        named_bar_sync(bar_id, 64);
+        const float m_new = fmaxf(m_run, fmaxf(mx, *x_other) * p.scale_log2);
+        alpha = ex2_approx(m_run - m_new);   // first block: exp2(-inf) = 0
+        m_run = m_new;
+        switch (ng) {
+          case 7: exp_groups5_np<7>(t_mine, nvr, p.scale_log2, m_new); break;
+          case 6: exp_groups5_np<6>(t_mine, nvr, p.scale_log2, m_new); break;
+          case 5: exp_groups5_np<5>(t_mine, nvr, p.scale_log2, m_new); break;
+          case 4: exp_groups5_np<4>(t_mine, nvr, p.scale_log2, m_new); break;
+          case 3: exp_groups5_np<3>(t_mine, nvr, p.scale_log2, m_new); break;
+          case 2: exp_groups5_np<2>(t_mine, nvr, p.scale_log2, m_new); break;
+          case 1: exp_groups5_np<1>(t_mine, nvr, p.scale_log2, m_new); break;
+          default: break;
+        }
+        // the exchange slot is rewritten in the next unit: both readers are past it (they arrive on the
+        // named barrier of the next unit only after this unit's read)
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(C_PFULL + g));
+
+      if (last_blk && lane == 0) tma_store_wait_read<0>();
+      mbar_wait_lean5(bar(C_OFULL + g), ph);
+      tc_fence_after();
+      if (live) {
+        uint32_t r[32];
+        uint32_t rl[8];
+        tmem_ld_32x32(t_lane + kOCol5 + half * 32, r);
+        tmem_ld_32x8(t_lane + kLCol5, rl);
+        tmem_ld_wait();
+        if (j == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o_acc[i] = __uint_as_float(r[i]);
+          l_acc = __uint_as_float(rl[0]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o_acc[i] = fmaf(o_acc[i], alpha, __uint_as_float(r[i]));
+          l_acc = fmaf(l_acc, alpha, __uint_as_float(rl[0]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(C_OREAD));
+      if (live && last_blk) {
+        float inv;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(l_acc));
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          uint4 o4;
+          o4.x = pack_bf16x2(o_acc[8 * jj + 0] * inv, o_acc[8 * jj + 1] * inv);
+          o4.y = pack_bf16x2(o_acc[8 * jj + 2] * inv, o_acc[8 * jj + 3] * inv);
+          o4.z = pack_bf16x2(o_acc[8 * jj + 4] * inv, o_acc[8 * jj + 5] * inv);
+          o4.w = pack_bf16x2(o_acc[8 * jj + 6] * inv, o_acc[8 * jj + 7] * inv);
+          *reinterpret_cast<uint4*>(stage_row + ((jj ^ sw) << 4)) = o4;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                       :
+                       : "l"(reinterpret_cast<uint64_t>(&tma_o)), "r"(stage_addr),
+                         "r"(desc.y * kDH5 + half * 32), "r"(desc.z * kQTile5 + rq * 32), "r"(desc.x)
+                       : "memory");
+          tma_store_commit();
+        }
+      }
+      if (++j == nblk) { j = 0; ++li; }
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 16) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 long long* g_attn5_dbg = nullptr;
 
 }  // namespace
@@ -492,6 +867,61 @@ int attn5_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, in
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long grid = p.total_items < sms ? p.total_items : sms;
   attn5_fwd_kernel<<<static_cast<unsigned>(grid), kThreads5, smem, stream>>>(tq, tk, tv, to, p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// N > 208, head dim 64: several KV blocks per item (online softmax), same two-group kernel structure.
+int attn5mb_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, int B, int H, int N,
+                        int dh, long long qkv_row_stride, long long qkv_batch_stride,
+                        long long out_row_stride, long long out_batch_stride, float scale, int reverse,
+                        cudaStream_t stream) {
+  if (!q || !k || !v || !out || B <= 0 || H <= 0 || N <= 0) return VT_ERR_ARG;
+  if (dh != kDH5 || N <= kMaxN5) return VT_ERR_UNSUPPORTED;
+  if ((qkv_row_stride % 8) || (qkv_batch_stride % 8) || (out_row_stride % 8) || (out_batch_stride % 8))
+    return VT_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+       reinterpret_cast<uintptr_t>(out)) & 15)
+    return VT_ERR_ALIGN;
+
+  Attn5MbParams p;
+  p.N = N;
+  p.H = H;
+  p.B = B;
+  p.nqt = (N + kQTile5 - 1) / kQTile5;
+  p.nblk = (N + kMaxN5 - 1) / kMaxN5;
+  const int bkv = (N + p.nblk - 1) / p.nblk;
+  p.bkv = (bkv + 15) & ~15;
+  if ((p.nblk - 1) * p.bkv >= N) return VT_ERR_UNSUPPORTED;   // the last block must hold at least one key
+  p.total_items = static_cast<long long>(B) * H * p.nqt;
+  if (p.total_items * p.nblk >= (1LL << 31)) return VT_ERR_UNSUPPORTED;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.reverse = reverse;
+  const int smem = 1024 + 2 * kQBytes5 + 4 * p.bkv * kDH5 * 2 + 16 * kStageBytes5 + kOnesBytes5 + 8 * C_NBARS + 8 +
+                   16 * kRing5 + 2 * 2 * kQTile5 * 4;
+  if (smem > kSmemLimit5) return VT_ERR_UNSUPPORTED;
+
+  const uint64_t cols = static_cast<uint64_t>(H) * dh;
+  CUtensorMap tq, tk, tv, to;
+  int rc = make_tmap_bf16_3d(&tq, q, cols, N, B, qkv_row_stride, qkv_batch_stride, kDH5, kQTile5, TMAP_SW_128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tk, k, cols, N, B, qkv_row_stride, qkv_batch_stride, kDH5, p.bkv, TMAP_SW_128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tv, v, cols, N, B, qkv_row_stride, qkv_batch_stride, kDH5, p.bkv, TMAP_SW_128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&to, out, cols, N, B, out_row_stride, out_batch_stride, 32, 32, TMAP_SW_64);
+  if (rc) return rc;
+
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn5mb_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    smem_set = smem;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long grid = p.total_items < sms ? p.total_items : sms;
+  attn5mb_fwd_kernel<<<static_cast<unsigned>(grid), kThreads5, smem, stream>>>(tq, tk, tv, to, p);
   return static_cast<int>(cudaGetLastError());
 }
 
