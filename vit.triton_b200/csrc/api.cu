@@ -144,10 +144,11 @@ int vt_gemm_strided(const void* A, const void* B, void* C, const void* bias, int
 int vt_flash_attn(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H,
                   int32_t N, int32_t dh, int64_t qkv_row_stride, int64_t qkv_batch_stride,
                   int64_t out_row_stride, int64_t out_batch_stride, float scale, void* stream) {
-  // Persistent kernels.  Head dim 64: attn5 (two de-phased softmax groups over double-buffered scores;
-  // one KV block for N <= 208, the online-softmax multi-block kernel beyond), default.  attn4 (one
-  // group of 16 warps) with VT_ATTN_IMPL=4 (N <= 208, or any N with VT_ATTN4_MULTIBLOCK=1).  Head
-  // dim 80: attn3 (two slots x two column halves).  VT_ATTN_IMPL=3 / 2 / 1 force attn3 / attn2 /
+  // Persistent kernels.  attn5 (two de-phased softmax groups over double-buffered scores) is the
+  // default: the single-block kernel for head dim 64 and N <= 208, the online-softmax multi-block
+  // kernel for longer sequences and for head dim 80 (ViT-H).  attn4 (one group of 16 warps) with
+  // VT_ATTN_IMPL=4 (N <= 208, or any N with VT_ATTN4_MULTIBLOCK=1); attn3 (two slots x two column
+  // halves, both head dims) with VT_ATTN_IMPL=3.  VT_ATTN_IMPL=3 / 2 / 1 force attn3 / attn2 /
   // the one-tile-per-CTA kernel.  The alternatives exist for A/B measurements.
   // (read on every call — a getenv is nothing next to a launch — so tests can exercise every variant)
   const char* e = getenv("VT_ATTN_IMPL");
@@ -155,7 +156,7 @@ int vt_flash_attn(const void* q, const void* k, const void* v, void* out, int32_
   if (impl == 5 && dh == 64 && N <= 208)
     return vt::attn5_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
                                  out_row_stride, out_batch_stride, scale, next_direction(), S(stream));
-  if (impl == 5 && dh == 64) {   // N > 208: several KV blocks per item, same two-group structure
+  if (impl == 5 && (dh == 64 || dh == 80)) {   // N > 208 and / or head dim 80: per-group unit streams
     const int rc = vt::attn5mb_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
                                            out_row_stride, out_batch_stride, scale, next_direction(), S(stream));
     if (rc != VT_ERR_UNSUPPORTED) return rc;

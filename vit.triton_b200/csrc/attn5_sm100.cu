@@ -507,22 +507,38 @@ __device__ __forceinline__ void exp_groups5_np(uint32_t a, int nv, float scale_l
   tmem_st_wait();
 }
 
+// Head dim 80 (ViT-H): 160-byte rows do not fit the 128-byte swizzle, so every Q/K/V tile is a
+// 64-column SWIZZLE_128B part plus a 16-column SWIZZLE_32B part ("tail"); Q K^T gets a fifth K step on
+// the tails, P V a second N = 16 MMA per K step into output columns [64, 80), and the row sums move
+// to TMEM columns [496, 512): O [416, 496) + sums fill the 512 columns exactly.
+template <int DH>
 __global__ void __launch_bounds__(kThreads5, 1)
 attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                    const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_o,
-                   const Attn5MbParams p) {
+                   const __grid_constant__ CUtensorMap tma_qt, const __grid_constant__ CUtensorMap tma_kt,
+                   const __grid_constant__ CUtensorMap tma_vt, const Attn5MbParams p) {
+  static_assert(DH == 64 || DH == 80, "head dim 64 or 80");
+  constexpr int kDT = DH - kDH5;                  // 0 or 16: columns of the SWIZZLE_32B tail
+  constexpr int kHalfCols = DH / 2;               // output columns per softmax thread
+  constexpr int kStage = 32 * kHalfCols * 2;      // staging bytes per warp
+  constexpr int kLCol = kOCol5 + DH;              // row sums
+  constexpr int kQTailBytes = kQTile5 * kDT * 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  const int kv_bytes = p.bkv * kDH5 * 2;
-  // same layout as attn5_fwd_kernel; buffers are indexed by GROUP
+  const int kv_bytes = p.bkv * kDH5 * 2;          // SWIZZLE_128B part of one K or V block
+  const int kv_tail = p.bkv * kDT * 2;            // SWIZZLE_32B part
+  // [Q x2][K x2][V x2][Q tails x2][K tails x2][V tails x2][staging][ones][barriers]...; buffers indexed by GROUP
   const uint32_t q_smem = smem_base;
   const uint32_t k_smem = q_smem + 2 * kQBytes5;
   const uint32_t v_smem = k_smem + 2 * kv_bytes;
-  const int stage_off = 2 * kQBytes5 + 4 * kv_bytes;
+  const uint32_t qt_smem = v_smem + 2 * kv_bytes;
+  const uint32_t kt_smem = qt_smem + 2 * kQTailBytes;
+  const uint32_t vt_smem = kt_smem + 2 * kv_tail;
+  const int stage_off = 2 * kQBytes5 + 4 * kv_bytes + 2 * kQTailBytes + 4 * kv_tail;
   const uint32_t stage_smem = smem_base + stage_off;
-  const int ones_off = stage_off + 16 * kStageBytes5;
+  const int ones_off = stage_off + 16 * kStage;
   const uint32_t ones_smem = smem_base + ones_off;
   const int bar_off = ones_off + kOnesBytes5;
   const uint32_t bar_base = smem_base + bar_off;
@@ -544,6 +560,11 @@ attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     tma_prefetch_desc(&tma_k);
     tma_prefetch_desc(&tma_v);
     tma_prefetch_desc(&tma_o);
+    if (kDT) {
+      tma_prefetch_desc(&tma_qt);
+      tma_prefetch_desc(&tma_kt);
+      tma_prefetch_desc(&tma_vt);
+    }
   }
   if (warp_idx == 0) {
     reinterpret_cast<uint4*>(smem_gen + ones_off)[lane] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -592,8 +613,11 @@ attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         mbar_wait(bar(C_QEMPTY + g), ph ^ 1u);
         if (elect_one_sync()) {
           ring[it & (kRing5 - 1)] = make_int4(img[g], head[g], qt, 0);
-          mbar_arrive_expect_tx(bar(C_QFULL + g), kQBytes5);
-          tma_load_3d(&tma_q, bar(C_QFULL + g), q_smem + g * kQBytes5, head[g] * kDH5, qt * kQTile5, img[g], kEvictFirst);
+          mbar_arrive_expect_tx(bar(C_QFULL + g), kQBytes5 + kQTailBytes);
+          tma_load_3d(&tma_q, bar(C_QFULL + g), q_smem + g * kQBytes5, head[g] * DH, qt * kQTile5, img[g], kEvictFirst);
+          if (kDT)
+            tma_load_3d(&tma_qt, bar(C_QFULL + g), qt_smem + g * kQTailBytes, head[g] * DH + kDH5, qt * kQTile5, img[g],
+                        kEvictFirst);
         }
         __syncwarp();
       }
@@ -604,14 +628,18 @@ attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
           if (it0 + g >= n_items) continue;
           mbar_wait(bar(C_KEMPTY + g), ph ^ 1u);
           if (elect_one_sync()) {
-            mbar_arrive_expect_tx(bar(C_KFULL + g), kv_bytes);
-            tma_load_3d(&tma_k, bar(C_KFULL + g), k_smem + g * kv_bytes, head[g] * kDH5, j * bkv, img[g], kEvictNormal);
+            mbar_arrive_expect_tx(bar(C_KFULL + g), kv_bytes + kv_tail);
+            tma_load_3d(&tma_k, bar(C_KFULL + g), k_smem + g * kv_bytes, head[g] * DH, j * bkv, img[g], kEvictNormal);
+            if (kDT)
+              tma_load_3d(&tma_kt, bar(C_KFULL + g), kt_smem + g * kv_tail, head[g] * DH + kDH5, j * bkv, img[g], kEvictNormal);
           }
           __syncwarp();
           mbar_wait(bar(C_VEMPTY + g), ph ^ 1u);
           if (elect_one_sync()) {
-            mbar_arrive_expect_tx(bar(C_VFULL + g), kv_bytes);
-            tma_load_3d(&tma_v, bar(C_VFULL + g), v_smem + g * kv_bytes, head[g] * kDH5, j * bkv, img[g], kEvictNormal);
+            mbar_arrive_expect_tx(bar(C_VFULL + g), kv_bytes + kv_tail);
+            tma_load_3d(&tma_v, bar(C_VFULL + g), v_smem + g * kv_bytes, head[g] * DH, j * bkv, img[g], kEvictNormal);
+            if (kDT)
+              tma_load_3d(&tma_vt, bar(C_VFULL + g), vt_smem + g * kv_tail, head[g] * DH + kDH5, j * bkv, img[g], kEvictNormal);
           }
           __syncwarp();
         }
@@ -635,6 +663,9 @@ attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
 #pragma unroll
         for (int k = 0; k < kDH5 / 16; ++k)
           umma_ss(tmem_base + g * kSCols5, qd + 2 * k, kd + 2 * k, idesc, k != 0 ? 1u : 0u);
+        if (kDT)   // fifth K step on the 16-column SWIZZLE_32B tiles (rows of 32 B, 8-row atoms of 256 B)
+          umma_ss(tmem_base + g * kSCols5, make_smem_desc(qt_smem + g * kQTailBytes, 0, 256, 6),
+                  make_smem_desc(kt_smem + g * kv_tail, 0, 256, 6), idesc, 1u);
         umma_commit(bar(C_SFULL + g));
         umma_commit(bar(C_KEMPTY + g));
         if (j == nblk - 1) umma_commit(bar(C_QEMPTY + g));
@@ -664,11 +695,13 @@ attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         const uint32_t idesc_l = make_idesc_bf16(kQTile5, 16, 0, 1);
         const uint64_t vd = make_desc_mnmajor_sw128(v_smem + g * kv_bytes, 1024);
         const uint64_t od = make_smem_desc(ones_smem, 256, 256, 6);
+        const uint64_t vtd = make_smem_desc(vt_smem + g * kv_tail, 256, 256, 6);   // MN-major, SWIZZLE_32B
         const uint32_t s_tmem = tmem_base + g * kSCols5;
-        for (int k = 0; k < n16; ++k) {
+        for (int k = 0; k < n16; ++k) {   // 16 keys: 2048 B of the main V tile, 512 B of the tail tile
           const uint32_t a_tmem = s_tmem + (k < ng0 ? 8 * k : 16 * ng0 + 8 * (k - ng0));
           umma_ts(tmem_base + kOCol5, a_tmem, vd + 128 * k, idesc, k != 0 ? 1u : 0u);
-          umma_ts(tmem_base + kLCol5, a_tmem, od, idesc_l, k != 0 ? 1u : 0u);
+          if (kDT) umma_ts(tmem_base + kOCol5 + kDH5, a_tmem, vtd + 32 * k, idesc_l, k != 0 ? 1u : 0u);
+          umma_ts(tmem_base + kLCol, a_tmem, od, idesc_l, k != 0 ? 1u : 0u);
         }
         umma_commit(bar(C_OFULL + g));
         umma_commit(bar(C_VEMPTY + g));
@@ -685,9 +718,10 @@ attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     const int rq = warp_idx & 3;
     const int row_in_tile = rq * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(rq * 32) << 16);
-    const uint32_t stage_addr = stage_smem + warp_idx * kStageBytes5;
-    uint8_t* stage_row = smem_gen + stage_off + warp_idx * kStageBytes5 + lane * 64;
-    const int sw = (lane >> 1) & 3;
+    // [32 rows x 64 B] SWIZZLE_64B (dh 64) or [32 rows x 80 B] unswizzled (dh 80)
+    const uint32_t stage_addr = stage_smem + warp_idx * kStage;
+    uint8_t* stage_row = smem_gen + stage_off + warp_idx * kStage + lane * (kHalfCols * 2);
+    const int sw = (kDT == 0) ? ((lane >> 1) & 3) : 0;
     const int bar_id = 1 + g * 4 + rq;
     float* x_mine = xm + (g * 2 + half) * kQTile5 + row_in_tile;
     const float* x_other = xm + (g * 2 + (half ^ 1)) * kQTile5 + row_in_tile;
@@ -702,7 +736,7 @@ attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     int4 desc = make_int4(0, 0, 0, 0);
     bool live = false;
     float m_run = -INFINITY, l_acc = 0.f;
-    float o_acc[32];
+    float o_acc[kHalfCols];
     int j = 0, li = 0;
     for (int lu = 0; lu < units; ++lu) {
       const uint32_t ph = static_cast<uint32_t>(lu) & 1u;
@@ -759,17 +793,27 @@ attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
       tc_fence_after();
       if (live) {
         uint32_t r[32];
+        uint32_t r8[8];
         uint32_t rl[8];
-        tmem_ld_32x32(t_lane + kOCol5 + half * 32, r);
-        tmem_ld_32x8(t_lane + kLCol5, rl);
+        tmem_ld_32x32(t_lane + kOCol5 + half * kHalfCols, r);          // my DH / 2 contiguous output columns
+        if (kDT) tmem_ld_32x8(t_lane + kOCol5 + half * kHalfCols + 32, r8);
+        tmem_ld_32x8(t_lane + kLCol, rl);
         tmem_ld_wait();
         if (j == 0) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) o_acc[i] = __uint_as_float(r[i]);
+          if (kDT) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o_acc[32 + i] = __uint_as_float(r8[i]);
+          }
           l_acc = __uint_as_float(rl[0]);
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) o_acc[i] = fmaf(o_acc[i], alpha, __uint_as_float(r[i]));
+          if (kDT) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o_acc[32 + i] = fmaf(o_acc[32 + i], alpha, __uint_as_float(r8[i]));
+          }
           l_acc = fmaf(l_acc, alpha, __uint_as_float(rl[0]));
         }
       }
@@ -780,7 +824,7 @@ attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         float inv;
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(l_acc));
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
+        for (int jj = 0; jj < kHalfCols / 8; ++jj) {
           uint4 o4;
           o4.x = pack_bf16x2(o_acc[8 * jj + 0] * inv, o_acc[8 * jj + 1] * inv);
           o4.y = pack_bf16x2(o_acc[8 * jj + 2] * inv, o_acc[8 * jj + 3] * inv);
@@ -794,7 +838,7 @@ attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
           asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                        :
                        : "l"(reinterpret_cast<uint64_t>(&tma_o)), "r"(stage_addr),
-                         "r"(desc.y * kDH5 + half * 32), "r"(desc.z * kQTile5 + rq * 32), "r"(desc.x)
+                         "r"(desc.y * DH + half * kHalfCols), "r"(desc.z * kQTile5 + rq * 32), "r"(desc.x)
                        : "memory");
           tma_store_commit();
         }
@@ -870,13 +914,60 @@ int attn5_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, in
   return static_cast<int>(cudaGetLastError());
 }
 
-// N > 208, head dim 64: several KV blocks per item (online softmax), same two-group kernel structure.
+// Head dim 64 with N > 208 (several KV blocks per item, online softmax) and head dim 80 with any N:
+// the two-group kernel with per-group unit streams.
+template <int DH>
+static int launch_attn5mb(const void* q, const void* k, const void* v, void* out, int B, int H, int N,
+                          long long qkv_row_stride, long long qkv_batch_stride, long long out_row_stride,
+                          long long out_batch_stride, const Attn5MbParams& p, cudaStream_t stream) {
+  constexpr int kDT = DH - kDH5;
+  constexpr int kStage = 32 * (DH / 2) * 2;
+  const int smem = 1024 + 2 * kQTile5 * DH * 2 + 4 * p.bkv * DH * 2 + 16 * kStage + kOnesBytes5 + 8 * C_NBARS + 8 +
+                   16 * kRing5 + 2 * 2 * kQTile5 * 4;
+  if (smem > kSmemLimit5) return VT_ERR_UNSUPPORTED;
+  const uint64_t cols = static_cast<uint64_t>(H) * DH;
+  CUtensorMap tq, tk, tv, to, tqt, tkt, tvt;
+  int rc = make_tmap_bf16_3d(&tq, q, cols, N, B, qkv_row_stride, qkv_batch_stride, kDH5, kQTile5, TMAP_SW_128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tk, k, cols, N, B, qkv_row_stride, qkv_batch_stride, kDH5, p.bkv, TMAP_SW_128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tv, v, cols, N, B, qkv_row_stride, qkv_batch_stride, kDH5, p.bkv, TMAP_SW_128);
+  if (rc) return rc;
+  if (kDT) {
+    rc = make_tmap_bf16_3d(&tqt, q, cols, N, B, qkv_row_stride, qkv_batch_stride, 16, kQTile5, TMAP_SW_32);
+    if (rc) return rc;
+    rc = make_tmap_bf16_3d(&tkt, k, cols, N, B, qkv_row_stride, qkv_batch_stride, 16, p.bkv, TMAP_SW_32);
+    if (rc) return rc;
+    rc = make_tmap_bf16_3d(&tvt, v, cols, N, B, qkv_row_stride, qkv_batch_stride, 16, p.bkv, TMAP_SW_32);
+    if (rc) return rc;
+    rc = make_tmap_bf16_3d(&to, out, cols, N, B, out_row_stride, out_batch_stride, DH / 2, 32, TMAP_SW_NONE);
+  } else {
+    tqt = tq; tkt = tk; tvt = tv;   // unused
+    rc = make_tmap_bf16_3d(&to, out, cols, N, B, out_row_stride, out_batch_stride, 32, 32, TMAP_SW_64);
+  }
+  if (rc) return rc;
+
+  auto kern = attn5mb_fwd_kernel<DH>;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    smem_set = smem;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long grid = p.total_items < sms ? p.total_items : sms;
+  kern<<<static_cast<unsigned>(grid), kThreads5, smem, stream>>>(tq, tk, tv, to, tqt, tkt, tvt, p);
+  return static_cast<int>(cudaGetLastError());
+}
+
 int attn5mb_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, int B, int H, int N,
                         int dh, long long qkv_row_stride, long long qkv_batch_stride,
                         long long out_row_stride, long long out_batch_stride, float scale, int reverse,
                         cudaStream_t stream) {
   if (!q || !k || !v || !out || B <= 0 || H <= 0 || N <= 0) return VT_ERR_ARG;
-  if (dh != kDH5 || N <= kMaxN5) return VT_ERR_UNSUPPORTED;
+  if (dh != 64 && dh != 80) return VT_ERR_UNSUPPORTED;
   if ((qkv_row_stride % 8) || (qkv_batch_stride % 8) || (out_row_stride % 8) || (out_batch_stride % 8))
     return VT_ERR_ALIGN;
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
@@ -896,33 +987,11 @@ int attn5mb_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, 
   if (p.total_items * p.nblk >= (1LL << 31)) return VT_ERR_UNSUPPORTED;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.reverse = reverse;
-  const int smem = 1024 + 2 * kQBytes5 + 4 * p.bkv * kDH5 * 2 + 16 * kStageBytes5 + kOnesBytes5 + 8 * C_NBARS + 8 +
-                   16 * kRing5 + 2 * 2 * kQTile5 * 4;
-  if (smem > kSmemLimit5) return VT_ERR_UNSUPPORTED;
-
-  const uint64_t cols = static_cast<uint64_t>(H) * dh;
-  CUtensorMap tq, tk, tv, to;
-  int rc = make_tmap_bf16_3d(&tq, q, cols, N, B, qkv_row_stride, qkv_batch_stride, kDH5, kQTile5, TMAP_SW_128);
-  if (rc) return rc;
-  rc = make_tmap_bf16_3d(&tk, k, cols, N, B, qkv_row_stride, qkv_batch_stride, kDH5, p.bkv, TMAP_SW_128);
-  if (rc) return rc;
-  rc = make_tmap_bf16_3d(&tv, v, cols, N, B, qkv_row_stride, qkv_batch_stride, kDH5, p.bkv, TMAP_SW_128);
-  if (rc) return rc;
-  rc = make_tmap_bf16_3d(&to, out, cols, N, B, out_row_stride, out_batch_stride, 32, 32, TMAP_SW_64);
-  if (rc) return rc;
-
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn5mb_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    smem_set = smem;
-  }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long grid = p.total_items < sms ? p.total_items : sms;
-  attn5mb_fwd_kernel<<<static_cast<unsigned>(grid), kThreads5, smem, stream>>>(tq, tk, tv, to, p);
-  return static_cast<int>(cudaGetLastError());
+  if (dh == 64)
+    return launch_attn5mb<64>(q, k, v, out, B, H, N, qkv_row_stride, qkv_batch_stride, out_row_stride,
+                              out_batch_stride, p, stream);
+  return launch_attn5mb<80>(q, k, v, out, B, H, N, qkv_row_stride, qkv_batch_stride, out_row_stride,
+                            out_batch_stride, p, stream);
 }
 
 }  // namespace vt
