@@ -119,6 +119,10 @@ def hf_cpu_images_per_sec(arch, batch, budget_s=15.0):
     returns (img/s from the median forward, threads, list of forward times)."""
     import torch
     from oracle import hf_oracle
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, OSError):
+        torch.set_num_threads(os.cpu_count() or 1)
     model = hf_oracle.build_hf(arch, seed=0)
     x = hf_oracle.make_input(arch, batch)
     times = []
@@ -142,6 +146,12 @@ def run_reference(args, arch, desc):
         return
     import torch
     from oracle import hf_oracle
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs on rank 0 alone and is
+    # meant to use every host thread it can
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, OSError):
+        torch.set_num_threads(os.cpu_count() or 1)
     sample_batch = 32
     model = hf_oracle.build_hf(arch, seed=0)
     x = hf_oracle.make_input(arch, sample_batch)
