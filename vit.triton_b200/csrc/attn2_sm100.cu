@@ -565,12 +565,8 @@ int attn2_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, in
                          32, TMAP_SW_128);
   if (rc) return rc;
 
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    smem_set = smem;
-  }
+  static int granted[kMaxDevices] = {0};
+  if (const int rc_attr = ensure_dynamic_smem(attn2_fwd_kernel, smem, granted)) return rc_attr;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -432,12 +432,8 @@ int launch_attn3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap
                  const CUtensorMap& tqt, const CUtensorMap& tkt, const CUtensorMap& tvt, const Attn3Params& p,
                  int smem, cudaStream_t stream) {
   auto kern = attn3_fwd_kernel<DH>;
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    smem_set = smem;
-  }
+  static int granted[kMaxDevices] = {0};
+  if (const int rc_attr = ensure_dynamic_smem(kern, smem, granted)) return rc_attr;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -567,14 +567,9 @@ int attn4_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, in
   rc = make_tmap_bf16_3d(&to, out, cols, N, B, out_row_stride, out_batch_stride, 16, 32, TMAP_SW_NONE);
   if (rc) return rc;
 
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn4_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn4_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    smem_set = smem;
-  }
+  static int granted_single[kMaxDevices] = {0}, granted_multi[kMaxDevices] = {0};
+  if (const int rc_attr = ensure_dynamic_smem(attn4_fwd_kernel<true>, smem, granted_single)) return rc_attr;
+  if (const int rc_attr = ensure_dynamic_smem(attn4_fwd_kernel<false>, smem, granted_multi)) return rc_attr;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

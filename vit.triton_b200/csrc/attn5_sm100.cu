@@ -900,12 +900,8 @@ int attn5_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, in
   rc = make_tmap_bf16_3d(&to, out, cols, N, B, out_row_stride, out_batch_stride, 32, 32, TMAP_SW_64);
   if (rc) return rc;
 
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn5_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    smem_set = smem;
-  }
+  static int granted[kMaxDevices] = {0};
+  if (const int rc_attr = ensure_dynamic_smem(attn5_fwd_kernel, smem, granted)) return rc_attr;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -948,12 +944,8 @@ static int launch_attn5mb(const void* q, const void* k, const void* v, void* out
   if (rc) return rc;
 
   auto kern = attn5mb_fwd_kernel<DH>;
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    smem_set = smem;
-  }
+  static int granted[kMaxDevices] = {0};
+  if (const int rc_attr = ensure_dynamic_smem(kern, smem, granted)) return rc_attr;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -318,12 +318,8 @@ int attn_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, int
 
   const int smem = 1024 + kQTile * dh * 2 + 2 * bkv * dh * 2 + 8 * B_COUNT + 16;
   auto kern = attn_fwd_tcgen05_kernel<64>;
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    smem_set = smem;
-  }
+  static int granted[kMaxDevices] = {0};
+  if (const int rc_attr = ensure_dynamic_smem(kern, smem, granted)) return rc_attr;
   dim3 grid((N + kQTile - 1) / kQTile, H, B);
   kern<<<grid, kAttnThreads, smem, stream>>>(tq, tk, tv, p);
   return static_cast<int>(cudaGetLastError());

@@ -26,6 +26,24 @@ enum : int {
 enum : int { VT_F32 = 0, VT_BF16 = 1, VT_U8 = 2 };
 
 // ----------------------------------------------------------------------------------------------
+// host: opt-in dynamic shared memory.  cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE
+// attribute; `granted` is the call site's own per-device cache (one static array per kernel).
+// ----------------------------------------------------------------------------------------------
+constexpr int kMaxDevices = 64;
+template <typename Kernel>
+inline int ensure_dynamic_smem(Kernel kernel, int bytes, int (&granted)[kMaxDevices]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+  if (bytes > granted[slot] || dev != slot) {
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    granted[slot] = bytes;
+  }
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
 // misc
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

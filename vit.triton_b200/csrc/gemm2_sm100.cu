@@ -487,12 +487,8 @@ template <int EPI>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
             const CUtensorMap& tr, const Gemm2Params& p, cudaStream_t stream) {
   auto kern = gemm2_bf16_kernel<EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
-  }
+  static int granted[kMaxDevices] = {0};
+  if (const int rc_attr = ensure_dynamic_smem(kern, kSmemBytes, granted)) return rc_attr;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   int clusters = num_sms2() / 2;
   if (tiles < clusters) clusters = tiles;

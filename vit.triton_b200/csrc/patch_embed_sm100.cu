@@ -381,12 +381,8 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const Patc
 template <typename TPix, bool kVec>
 int launch_patch(const CUtensorMap& tw, const PatchParams& p, dim3 grid, cudaStream_t stream) {
   auto kern = patch_embed_tcgen05_kernel<TPix, kVec>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PE_SMEM);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
-  }
+  static int granted[kMaxDevices] = {0};
+  if (const int rc_attr = ensure_dynamic_smem(kern, PE_SMEM, granted)) return rc_attr;
   kern<<<grid, PE_THREADS, PE_SMEM, stream>>>(tw, p);
   return static_cast<int>(cudaGetLastError());
 }
