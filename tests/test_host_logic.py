@@ -56,6 +56,48 @@ def test_packed_qkv_layout_matches_hf(arch):
     assert torch.allclose(emb.posb[1:], pos[1:] + hsd["embeddings.patch_embeddings.projection.bias"])
 
 
+@pytest.mark.parametrize("arch", ["tiny-b", "tiny-h"])
+def test_uint8_packing_folds_the_image_processor(arch):
+    """pack_embeddings_u8: raw bytes against the re-ordered, scaled weight + shifted bias table equal
+    the patch projection of the rescaled / normalised pixels (what the uint8 kernel path computes)."""
+    a = hf_oracle.ARCHS[arch]
+    model = VIT(**hf_oracle.vit_kwargs(arch))
+    with torch.no_grad():
+        for p_ in model.parameters():
+            p_.copy_(torch.randn_like(p_) * 0.05)
+    emb = model.embeddings
+    mean, std, r = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225), 1.0 / 255.0
+    pk = packing.pack_embeddings_u8(emb, mean, std, r)
+    S, P, D = a["image_size"], a["patch_size"], a["hidden_size"]
+    g = torch.Generator().manual_seed(5)
+    x = torch.randint(0, 256, (2, S, S, 3), generator=g, dtype=torch.uint8)
+    # patches of the NHWC bytes in (i, j, c) order: [B, n, P*P*3]
+    n = S // P
+    patches = x.float().reshape(2, n, P, n, P, 3).permute(0, 1, 3, 2, 4, 5).reshape(2, n * n, P * P * 3)
+    got = patches @ pk.w[:, :pk.K].float().t() + pk.posb[1:]
+    xn = (x.float() * r - torch.tensor(mean)) / torch.tensor(std)
+    want = torch.nn.functional.conv2d(xn.permute(0, 3, 1, 2), emb.projection.weight.float(),
+                                      emb.projection.bias.float(), stride=P).flatten(2).transpose(1, 2)
+    want = want + emb.position_embeddings.float()[0, 1:]
+    assert torch.allclose(got, want, atol=2e-3, rtol=1e-4), (got - want).abs().max()
+    assert torch.allclose(pk.posb[0], (emb.cls_token.float().reshape(-1) + emb.position_embeddings.float()[0, 0]))
+
+
+def test_pooler_weights_load_transposed():
+    """VIT(add_pooling_layer=True): pooler.dense is filled from HF's (out, in) weight as (in, out); the
+    default model has no pooler and keeps the reference's 990-key state dict."""
+    from transformers import ViTConfig, ViTModel
+    arch = "tiny-b"
+    torch.manual_seed(1)
+    hf = ViTModel(ViTConfig(**hf_oracle.ARCHS[arch]), add_pooling_layer=True).eval()
+    model = VIT(**hf_oracle.vit_kwargs(arch), add_pooling_layer=True)
+    transfer_pretrained_weights(hf, model, verbose=False)
+    assert torch.equal(model.pooler.dense.weight, hf.pooler.dense.weight.t())
+    assert torch.equal(model.pooler.dense.bias, hf.pooler.dense.bias)
+    plain = VIT(**hf_oracle.vit_kwargs(arch))
+    assert plain.pooler is None and not any(k.startswith("pooler") for k in plain.state_dict())
+
+
 def test_packed_cache_invalidation():
     model = VIT(**hf_oracle.vit_kwargs("tiny-b"))
     mha = model.encoder.layer[0].attention
