@@ -203,7 +203,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from oracle import hf_oracle            # cpu_baseline leg + architecture table only
+    from vit import configs
     from vit.kernels import _lib
     from vit.parallel import DataParallelVIT
     from vit.vit import VIT
@@ -218,10 +218,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
-    a = hf_oracle.ARCHS[arch]
+    a = configs.ARCHS[arch]
     # random-init weights of the named architecture (no network for checkpoints), same on all ranks
     torch.manual_seed(0)
-    model = VIT(**hf_oracle.vit_kwargs(arch))
+    model = VIT(**configs.vit_kwargs(arch))
     with torch.no_grad():
         for p in model.parameters():
             if p.dim() > 1:

@@ -3,7 +3,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "vit.triton_b200"))
 import torch
-from oracle import hf_oracle
+from vit import configs as hf_oracle   # architecture table only
 from vit import vit as V
 arch = "vit-b16-224"
 m = V.VIT(**hf_oracle.vit_kwargs(arch)).to("cuda", torch.bfloat16)
