@@ -109,10 +109,13 @@ template <bool MASKED>
 __device__ __forceinline__ void exp_group5(const uint32_t (&r)[16], uint32_t dst, int nv_in_group, float scale_log2,
                                            float m) {
   uint32_t pk[8];
+  const float2 sc2 = make_float2(scale_log2, scale_log2), nm2 = make_float2(-m, -m);
 #pragma unroll
   for (int i = 0; i < 16; i += 2) {
-    float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), scale_log2, -m));
-    float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m));
+    // one FFMA2 (sm_100 f32x2) for the two arguments
+    const float2 a2 = __ffma2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sc2, nm2);
+    float p0 = ex2_approx(a2.x);
+    float p1 = ex2_approx(a2.y);
     if (MASKED) {
       if (i >= nv_in_group) p0 = 0.f;
       if (i + 1 >= nv_in_group) p1 = 0.f;
