@@ -128,7 +128,8 @@ layernorm_rows_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
 
 // bf16 rows kept PACKED in registers (VPL x 4 registers instead of VPL x 8 unpacked floats) and
 // unpacked in each of the three passes: <= 32 registers per thread, i.e. 64 resident warps per SM
-// instead of 40 for layernorm_rows_kernel.  Same arithmetic, same bits.
+// instead of 40 for layernorm_rows_kernel.  Same formula; the sums run over even / odd elements
+// separately (packed pairs), so the last bit can differ from layernorm_rows_kernel.
 template <int VPL>
 __global__ void __launch_bounds__(256, 8)
 layernorm_bf16_packed_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
@@ -147,33 +148,36 @@ layernorm_bf16_packed_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfl
     const int vi = lane + i * 32;
     d[i] = (vi < nvec) ? xr[vi] : make_uint4(0u, 0u, 0u, 0u);
   }
-  float sum = 0.f;
+  // all arithmetic on packed fp32 pairs (FFMA2, sm_100 f32x2): the kernel is bound by instruction issue
+  auto up = [](uint32_t w) { return make_float2(bf16_lo(w), bf16_hi(w)); };
+  float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     if (lane + i * 32 < nvec) {
-      sum += bf16_lo(d[i].x); sum += bf16_hi(d[i].x); sum += bf16_lo(d[i].y); sum += bf16_hi(d[i].y);
-      sum += bf16_lo(d[i].z); sum += bf16_hi(d[i].z); sum += bf16_lo(d[i].w); sum += bf16_hi(d[i].w);
+      s2 = __fadd2_rn(s2, up(d[i].x)); s2 = __fadd2_rn(s2, up(d[i].y));
+      s2 = __fadd2_rn(s2, up(d[i].z)); s2 = __fadd2_rn(s2, up(d[i].w));
     }
   }
-  const float mean = warp_sum(sum) / static_cast<float>(dim);
-  float sq = 0.f;
-  auto acc = [&](float v) { const float c = v - mean; sq += c * c; };
+  const float mean = warp_sum(s2.x + s2.y) / static_cast<float>(dim);
+  const float2 nmean = make_float2(-mean, -mean);
+  float2 q2 = make_float2(0.f, 0.f);
+  auto acc = [&](uint32_t w) { const float2 c = __fadd2_rn(up(w), nmean); q2 = __ffma2_rn(c, c, q2); };
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     if (lane + i * 32 < nvec) {
-      acc(bf16_lo(d[i].x)); acc(bf16_hi(d[i].x)); acc(bf16_lo(d[i].y)); acc(bf16_hi(d[i].y));
-      acc(bf16_lo(d[i].z)); acc(bf16_hi(d[i].z)); acc(bf16_lo(d[i].w)); acc(bf16_hi(d[i].w));
+      acc(d[i].x); acc(d[i].y); acc(d[i].z); acc(d[i].w);
     }
   }
-  const float var = warp_sum(sq) / static_cast<float>(dim);
+  const float var = warp_sum(q2.x + q2.y) / static_cast<float>(dim);
   const float rstd = 1.0f / sqrtf(var + eps);
+  const float2 rstd2 = make_float2(rstd, rstd);
   uint4* orow = reinterpret_cast<uint4*>(out + row * out_stride);
   const uint4* gp = reinterpret_cast<const uint4*>(gamma);
   const uint4* bp = reinterpret_cast<const uint4*>(beta);
   auto nrm = [&](uint32_t v, uint32_t g, uint32_t b) {
-    const float lo = bf16_lo(g) * ((bf16_lo(v) - mean) * rstd) + bf16_lo(b);
-    const float hi = bf16_hi(g) * ((bf16_hi(v) - mean) * rstd) + bf16_hi(b);
-    return pack_bf16x2(lo, hi);
+    const float2 t = __fmul2_rn(__fadd2_rn(up(v), nmean), rstd2);
+    const float2 o = __ffma2_rn(up(g), t, up(b));
+    return pack_bf16x2(o.x, o.y);
   };
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
