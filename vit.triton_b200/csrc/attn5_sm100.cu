@@ -399,13 +399,18 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       // stage this warp's [32 rows x 32 columns] as a SWIZZLE_64B tile and TMA-store it (the staging
       // tile is free: lane 0 waited for the previous store above, the __syncwarp after the O read
       // ordered that before every lane's writes)
+      const float2 inv2 = make_float2(inv, inv);
+      auto scaled = [&](int i) {   // two output columns, one FMUL2
+        const float2 o = __fmul2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), inv2);
+        return pack_bf16x2(o.x, o.y);
+      };
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         uint4 o4;
-        o4.x = pack_bf16x2(__uint_as_float(r[8 * jj + 0]) * inv, __uint_as_float(r[8 * jj + 1]) * inv);
-        o4.y = pack_bf16x2(__uint_as_float(r[8 * jj + 2]) * inv, __uint_as_float(r[8 * jj + 3]) * inv);
-        o4.z = pack_bf16x2(__uint_as_float(r[8 * jj + 4]) * inv, __uint_as_float(r[8 * jj + 5]) * inv);
-        o4.w = pack_bf16x2(__uint_as_float(r[8 * jj + 6]) * inv, __uint_as_float(r[8 * jj + 7]) * inv);
+        o4.x = scaled(8 * jj + 0);
+        o4.y = scaled(8 * jj + 2);
+        o4.z = scaled(8 * jj + 4);
+        o4.w = scaled(8 * jj + 6);
         *reinterpret_cast<uint4*>(stage_row + ((jj ^ sw) << 4)) = o4;
       }
       fence_proxy_async_smem();
@@ -811,11 +816,22 @@ attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
           }
           l_acc = __uint_as_float(rl[0]);
         } else {
+          const float2 al2 = make_float2(alpha, alpha);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[i] = fmaf(o_acc[i], alpha, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; i += 2) {
+            const float2 o = __ffma2_rn(make_float2(o_acc[i], o_acc[i + 1]), al2,
+                                        make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+            o_acc[i] = o.x;
+            o_acc[i + 1] = o.y;
+          }
           if (kDT) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o_acc[32 + i] = fmaf(o_acc[32 + i], alpha, __uint_as_float(r8[i]));
+            for (int i = 0; i < 8; i += 2) {
+              const float2 o = __ffma2_rn(make_float2(o_acc[32 + i], o_acc[33 + i]), al2,
+                                          make_float2(__uint_as_float(r8[i]), __uint_as_float(r8[i + 1])));
+              o_acc[32 + i] = o.x;
+              o_acc[33 + i] = o.y;
+            }
           }
           l_acc = fmaf(l_acc, alpha, __uint_as_float(rl[0]));
         }
@@ -826,13 +842,18 @@ attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
       if (live && last_blk) {
         float inv;
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(l_acc));
+        const float2 inv2 = make_float2(inv, inv);
+        auto scaled = [&](int i) {
+          const float2 o = __fmul2_rn(make_float2(o_acc[i], o_acc[i + 1]), inv2);
+          return pack_bf16x2(o.x, o.y);
+        };
 #pragma unroll
         for (int jj = 0; jj < kHalfCols / 8; ++jj) {
           uint4 o4;
-          o4.x = pack_bf16x2(o_acc[8 * jj + 0] * inv, o_acc[8 * jj + 1] * inv);
-          o4.y = pack_bf16x2(o_acc[8 * jj + 2] * inv, o_acc[8 * jj + 3] * inv);
-          o4.z = pack_bf16x2(o_acc[8 * jj + 4] * inv, o_acc[8 * jj + 5] * inv);
-          o4.w = pack_bf16x2(o_acc[8 * jj + 6] * inv, o_acc[8 * jj + 7] * inv);
+          o4.x = scaled(8 * jj + 0);
+          o4.y = scaled(8 * jj + 2);
+          o4.z = scaled(8 * jj + 4);
+          o4.w = scaled(8 * jj + 6);
           *reinterpret_cast<uint4*>(stage_row + ((jj ^ sw) << 4)) = o4;
         }
         fence_proxy_async_smem();

@@ -316,11 +316,13 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const Patc
       if (e_valid && col < p.D) {
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          v[4 * i + 0] = __uint_as_float(rr[4 * i + 0]) + pb_cur[i].x;
-          v[4 * i + 1] = __uint_as_float(rr[4 * i + 1]) + pb_cur[i].y;
-          v[4 * i + 2] = __uint_as_float(rr[4 * i + 2]) + pb_cur[i].z;
-          v[4 * i + 3] = __uint_as_float(rr[4 * i + 3]) + pb_cur[i].w;
+        for (int i = 0; i < 4; ++i) {   // packed fp32 pairs: one FADD2 per two columns
+          const float2 lo = __fadd2_rn(make_float2(__uint_as_float(rr[4 * i + 0]), __uint_as_float(rr[4 * i + 1])),
+                                       make_float2(pb_cur[i].x, pb_cur[i].y));
+          const float2 hi = __fadd2_rn(make_float2(__uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3])),
+                                       make_float2(pb_cur[i].z, pb_cur[i].w));
+          v[4 * i + 0] = lo.x; v[4 * i + 1] = lo.y;
+          v[4 * i + 2] = hi.x; v[4 * i + 3] = hi.y;
         }
         const bool full_chunk = col + kStep <= p.D;
         if (p.out_f32) {
