@@ -43,7 +43,6 @@ _FUSED = True
 # +10 us fc2), but under the sustained power cap the forward is 1.3-2.3 % faster (tools/fold_ab.py:
 # 9.55 -> 9.33, 9.64 -> 9.52, 9.62 -> 9.45 ms): 12 launches and 1.9 GB of activation traffic less.
 _FOLD_LN = True
-_FOLD_LN_MLP = False   # layernorm_after -> fc1 fold, see set_layernorm_folding
 
 
 def set_fused(enabled: bool) -> None:
@@ -57,12 +56,11 @@ def fused_enabled() -> bool:
     return _FUSED
 
 
-def set_layernorm_folding(enabled: bool, mlp: bool = False) -> None:
+def set_layernorm_folding(enabled: bool) -> None:
     """Toggle folding of layernorm_before into the QKV GEMM epilogue (default ON, see the note at
     _FOLD_LN; only affects the fused bf16 path).  Off = 7 launches per block instead of 6."""
-    global _FOLD_LN, _FOLD_LN_MLP
+    global _FOLD_LN
     _FOLD_LN = bool(enabled)
-    _FOLD_LN_MLP = bool(enabled and mlp)
 
 
 class LinearWithBias(nn.Module):
@@ -187,14 +185,8 @@ class Transformer(packing.PackedMixin, nn.Module):
             pk = self.packed("folded")
             qkv = packing.linear_ln(x, pk.wqkv, pk.bqkv, pk.cqkv, ln1_stats, self.layernorm_before.eps)
         ctx = flash_attention(qkv, self.num_heads, 1.0 / math.sqrt(self.d_out))
-        if _FOLD_LN_MLP:
-            pk = self.packed("folded")
-            stats2 = torch.empty((x.shape[0] * x.shape[1], self.d_in // 64, 2), device=x.device, dtype=torch.float32)
-            res = packing.linear_res_stats(ctx, att.wo, att.bo, x, stats2)
-            mid = packing.linear_ln(res, pk.w1, pk.b1, pk.c1, stats2, self.layernorm_after.eps, gelu=True)
-        else:
-            res = packing.linear(ctx, att.wo, att.bo, residual=x)
-            mid = packing.linear(self.layernorm_after(res), mlp.w1, mlp.b1, gelu=True)
+        res = packing.linear(ctx, att.wo, att.bo, residual=x)
+        mid = packing.linear(self.layernorm_after(res), mlp.w1, mlp.b1, gelu=True)
         stats = torch.empty((x.shape[0] * x.shape[1], self.d_in // 64, 2), device=x.device, dtype=torch.float32)
         out = packing.linear_res_stats(mid, mlp.w2, mlp.b2, res, stats)
         return out, stats
