@@ -274,13 +274,23 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     };
     if (n_items > 0) issue_scores(0);
     if (n_items > 1) issue_scores(1);
+#ifdef VT_ATTN5_DBG
+    unsigned macc[4] = {0, 0, 0, 0};
+    unsigned mt = static_cast<unsigned>(clock());
+#define VT_MTICK(i) { const unsigned t_ = static_cast<unsigned>(clock()); macc[i] += t_ - mt; mt = t_; }
+#else
+#define VT_MTICK(i)
+#endif
     for (int v = 0; v < n_items; ++v) {
       const int b = v & 1;
       const uint32_t ph = (static_cast<uint32_t>(v) >> 1) & 1u;
       // ---- O_v = P_v V_v and the row sums P_v 1
       mbar_wait(bar(C_VFULL + b), ph);
+      VT_MTICK(0)
       if (v > 0) mbar_wait(bar(C_OREAD), static_cast<uint32_t>(v - 1) & 1u);   // O columns free
+      VT_MTICK(1)
       mbar_wait(bar(C_PFULL + b), ph);
+      VT_MTICK(2)
       tc_fence_after();
       if (elect_one_sync()) {
         const uint32_t idesc = make_idesc_bf16(kQTile5, kDH5, 0, 1);
@@ -299,7 +309,15 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       }
       __syncwarp();
       if (v + 2 < n_items) issue_scores(v + 2);
+      VT_MTICK(3)
     }
+#ifdef VT_ATTN5_DBG
+    if (p.dbg != nullptr && lane == 0) {
+      long long* d = p.dbg + (2LL * gridDim.x + blockIdx.x) * 8;
+      for (int i = 0; i < 4; ++i) d[i] = macc[i];
+    }
+#endif
+#undef VT_MTICK
   } else {
     // ------------------------------------------------------------------ softmax warps
     const int g = warp_idx >> 3;             // group = score buffer = item parity
