@@ -19,6 +19,8 @@
 // buffer before the accumulator is ready, so neither residual reads nor output writes go through
 // per-thread global accesses (the v1 row-per-thread stores made the epilogue the bottleneck:
 // profiles/r01_*).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tensormap.h"
 
@@ -30,7 +32,6 @@ constexpr int BM = 128;          // rows per CTA (pair tile = 256)
 constexpr int BN = 256;          // tile columns
 constexpr int BNH = 128;         // Bt rows loaded per CTA
 constexpr int BK = 64;
-constexpr int kStages = 5;
 #ifndef VT_EPI_WARPS
 #define VT_EPI_WARPS 8
 #endif
@@ -43,10 +44,28 @@ constexpr int kBBytes = BNH * BK * 2;
 constexpr int kStageBytes = kABytes + kBBytes;          // 32 KB
 constexpr int kChunkCols = 64;
 constexpr int kStagingBytes = 32 * kChunkCols * 2;      // 4 KB: 32 rows x 64 bf16
-constexpr int kChunks = kColsPerWarp / kChunkCols;          // staging buffers (= chunks) per warp
-constexpr int kEpiBytes = kEpiWarps * kChunks * kStagingBytes; // 64 KB
-constexpr int kNumBars = 2 * kStages + 4 + kChunks * kEpiWarps;
-constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiBytes + 8 * kNumBars + 16;
+constexpr int kChunks = kColsPerWarp / kChunkCols;          // chunks per warp
+
+// Shared-memory split between operand stages and epilogue staging (227 KB in all):
+//   5 stages + one staging buffer per chunk (no reuse inside a tile)   -> epilogue-heavy launches
+//   6 stages + ONE staging buffer per epilogue warp (reused per chunk)  -> everything else
+// Five 32 KB stages cover ~3000 cycles of operand latency under load and the MMA issuer still waits
+// for operands 40 % of the time; the sixth stage shortens a QKV tile from 7313 to 6837 cycles and an
+// fc2 tile from 27073 to 26197, but serialising the two chunks of a warp on one staging buffer costs
+// the GELU epilogue (+3.8 %), the K = 768 residual epilogue (+4.2 %) and the LayerNorm-fold epilogue
+// (137 -> 151 us per launch) more than it gives.  In the C2 forward: plain QKV 117.7 -> 112.1 us,
+// fc2 + statistics 166.1 -> 162.8 us (CUPTI, same box).
+template <int kStagesT, int kStageBufsT>
+struct G2Cfg {
+  static constexpr int kStages = kStagesT;
+  static constexpr int kStageBufs = kStageBufsT;
+  static constexpr int kEpiBytes = kEpiWarps * kStageBufs * kStagingBytes;
+  static constexpr int kNumBars = 2 * kStages + 4 + kChunks * kEpiWarps;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiBytes + 8 * kNumBars + 16;
+  static_assert(kSmemBytes <= 232448, "over the 227 KB shared-memory limit");
+};
+using G2Deep = G2Cfg<6, 1>;
+using G2Wide = G2Cfg<5, 2>;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;             // clears the CTA-rank bit of a cluster smem address
 
 enum : int { EPI_GELU = 1, EPI_RES = 2, EPI_LNF = 4, EPI_STATS = 8 };
@@ -145,11 +164,15 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
 
 __device__ __forceinline__ float2 gelu_epi2(float2 x) { return gelu_erf_bf16_x2(x); }
 
-template <int EPI>
+template <int EPI, typename Cfg>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const __grid_constant__ CUtensorMap tma_out,
                   const __grid_constant__ CUtensorMap tma_res, const Gemm2Params p) {
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kStageBufs = Cfg::kStageBufs;
+  constexpr int kEpiBytes = Cfg::kEpiBytes;
+  constexpr int kNumBars = Cfg::kNumBars;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -292,8 +315,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     uint8_t* stage_gen[kChunks];
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) {
-      stage_buf[c] = epi_addr + (kChunks * ew + c) * kStagingBytes;
-      stage_gen[c] = smem_gen + kStages * kStageBytes + (kChunks * ew + c) * kStagingBytes;
+      stage_buf[c] = epi_addr + (kStageBufs * ew + (c % kStageBufs)) * kStagingBytes;
+      stage_gen[c] = smem_gen + kStages * kStageBytes + (kStageBufs * ew + (c % kStageBufs)) * kStagingBytes;
     }
     const int sw = lane & 7;   // swizzle phase of this thread's staging row
     int as = 0;
@@ -309,7 +332,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       if (EPI & EPI_RES) {
         if (lane == 0) {
 #pragma unroll
-          for (int c = 0; c < kChunks; ++c) {
+          for (int c = 0; c < kStageBufs; ++c) {
             mbar_arrive_expect_tx(res_bar(ew, c), kStagingBytes);
             tma_load_2d(&tma_res, res_bar(ew, c), stage_buf[c], col0 + c * kChunkCols, row0,
                         kEvictFirst);
@@ -346,6 +369,17 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       for (int c = 0; c < kChunks; ++c) {
         const int col = col0 + c * kChunkCols;
         const bool live = col < p.N;   // warp-uniform: chunk not entirely right of the matrix
+        if (kStageBufs < kChunks && c >= kStageBufs) {
+          // the staging buffer is shared with an earlier chunk of this tile: its store must have read it
+          if (lane == 0) {
+            tma_store_wait_read<0>();
+            if (EPI & EPI_RES) {
+              mbar_arrive_expect_tx(res_bar(ew, c), kStagingBytes);
+              tma_load_2d(&tma_res, res_bar(ew, c), stage_buf[c], col, row0, kEvictFirst);
+            }
+          }
+          __syncwarp();
+        }
         if (EPI & EPI_RES) mbar_wait(res_bar(ew, c), rphase);
         uint8_t* rowp = stage_gen[c] + lane * 128;
         float2 st_sum2 = make_float2(0.f, 0.f), st_sq2 = make_float2(0.f, 0.f);   // even / odd columns
@@ -484,16 +518,16 @@ int num_sms2() {
   return g_num_sms2;
 }
 
-template <int EPI>
+template <int EPI, typename Cfg>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
             const CUtensorMap& tr, const Gemm2Params& p, cudaStream_t stream) {
-  auto kern = gemm2_bf16_kernel<EPI>;
+  auto kern = gemm2_bf16_kernel<EPI, Cfg>;
   static int granted[kMaxDevices] = {0};
-  if (const int rc_attr = ensure_dynamic_smem(kern, kSmemBytes, granted)) return rc_attr;
+  if (const int rc_attr = ensure_dynamic_smem(kern, Cfg::kSmemBytes, granted)) return rc_attr;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   int clusters = num_sms2() / 2;
   if (tiles < clusters) clusters = tiles;
-  kern<<<2 * clusters, kThreads, kSmemBytes, stream>>>(ta, tb, to, tr, p);
+  kern<<<2 * clusters, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, tr, p);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -550,12 +584,20 @@ int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long l
   p.ln_parts = ln_dim / 64;
   p.stats_out = stats_out;
   p.dbg = g_dbg_buffer;
-  if (rowstats) return gelu ? launch2<EPI_LNF | EPI_GELU>(ta, tb, to, tr, p, stream)
-                            : launch2<EPI_LNF>(ta, tb, to, tr, p, stream);
-  if (gelu) return launch2<EPI_GELU>(ta, tb, to, tr, p, stream);
-  if (residual) return stats_out ? launch2<EPI_RES | EPI_STATS>(ta, tb, to, tr, p, stream)
-                                 : launch2<EPI_RES>(ta, tb, to, tr, p, stream);
-  return launch2<0>(ta, tb, to, tr, p, stream);
+  // Shared-memory split per epilogue (see G2Cfg): GELU, LayerNorm-fold and short-K residual epilogues
+  // keep two staging buffers per warp, everything else takes the sixth operand stage.  VT_GEMM_STAGES=5|6 forces one.
+  static const int forced = [] {
+    const char* e = getenv("VT_GEMM_STAGES");
+    return (e && (e[0] == '5' || e[0] == '6')) ? (e[0] - '0') : 0;
+  }();
+  const bool epilogue_heavy = gelu || rowstats != nullptr || (residual && K < 2048);
+  const bool deep = forced ? (forced == 6) : !epilogue_heavy;
+#define VT_G2_LAUNCH(E) (deep ? launch2<E, G2Deep>(ta, tb, to, tr, p, stream) : launch2<E, G2Wide>(ta, tb, to, tr, p, stream))
+  if (rowstats) return gelu ? VT_G2_LAUNCH(EPI_LNF | EPI_GELU) : VT_G2_LAUNCH(EPI_LNF);
+  if (gelu) return VT_G2_LAUNCH(EPI_GELU);
+  if (residual) return stats_out ? VT_G2_LAUNCH(EPI_RES | EPI_STATS) : VT_G2_LAUNCH(EPI_RES);
+  return VT_G2_LAUNCH(0);
+#undef VT_G2_LAUNCH
 }
 
 }  // namespace vt
