@@ -66,12 +66,12 @@ int vt_gemm_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, void* 
 
 /* K1 with LayerNorm folded into the epilogue and/or row statistics emitted for the next fold (bf16 out).
  *   rowstats != NULL (with colsum): A is the UN-normalised activation; row m's (sum, sumsq) over its
- *     ln_dim elements is given as ln_dim/64 partial pairs rowstats[(m*(ln_dim/64) + i)*2 .. +1]
- *     (summed in index order: bit-reproducible); ln_dim % 64 == 0; Bt must carry gamma
+ *     ln_dim elements is given as ln_dim/128 partial pairs rowstats[(m*(ln_dim/128) + i)*2 .. +1]
+ *     (summed in index order: bit-reproducible); ln_dim % 128 == 0; Bt must carry gamma
  *     (Bt[n,k] = W[n,k] * gamma[k]), bias must carry beta (bias[n] + sum_k beta[k] W[n,k]) and
  *     colsum[n] = sum_k Bt[n,k]:   out = rstd_m * acc - rstd_m * mean_m * colsum_n + bias_n  (then GELU).
- *   stats_out != NULL (needs residual, N % 64 == 0): writes the (sum, sumsq) of every 64-column chunk
- *     of every output row to stats_out[(m*(N/64) + chunk)*2 .. +1] — the rowstats layout above.
+ *   stats_out != NULL (needs residual, N % 128 == 0): writes the (sum, sumsq) of every 128-column group
+ *     of every output row to stats_out[(m*(N/128) + group)*2 .. +1] — the rowstats layout above.
  * Replaces layernorm_triton (vit/kernels/layernorm.py:90-127) + matmul_triton for the
  * LN -> dense pairs of Transformer.forward (vit/vit.py:133-144). */
 int vt_gemm_bf16_ln(const void* A, int64_t lda, const void* Bt, int64_t ldb, void* out, int64_t ldo,

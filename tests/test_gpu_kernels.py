@@ -372,7 +372,7 @@ def test_pool_cls():
 
 
 # ------------------------------------------------------------------------------- LayerNorm folded into the GEMM
-@pytest.mark.parametrize("M,K,N", [(197 * 5, 768, 2304), (300, 128, 512), (129, 1280, 264)])
+@pytest.mark.parametrize("M,K,N", [(197 * 5, 768, 2304), (300, 128, 512), (129, 1280, 264), (260, 384, 640), (70, 1536, 256)])
 @pytest.mark.parametrize("gelu", [False, True])
 def test_gemm_layernorm_fold(M, K, N, gelu):
     """vt_gemm_bf16_ln == dense(LayerNorm(x)) with the normalisation applied in the epilogue."""
@@ -386,8 +386,8 @@ def test_gemm_layernorm_fold(M, K, N, gelu):
     bias = torch.randn(N, device=dev())
     w_fold, b_fold, colsum = packing._fold_layernorm(w_nk, bias, ln)
     xf = x.float()[0]
-    xc = xf.view(M, K // 64, 64)
-    stats = torch.stack([xc.sum(-1), (xc * xc).sum(-1)], dim=2).contiguous()      # (M, K/64, 2) partials
+    xc = xf.view(M, K // 128, 128)
+    stats = torch.stack([xc.sum(-1), (xc * xc).sum(-1)], dim=2).contiguous()      # (M, K/128, 2) partials
     got = packing.linear_ln(x, w_fold, b_fold, colsum, stats, 1e-12, gelu=gelu)
     want = F.layer_norm(xf, (K,), ln.weight, ln.bias, 1e-12) @ w_nk.float().t() + bias
     if gelu:
@@ -402,11 +402,11 @@ def test_gemm_row_stats_output():
     w_nk = (torch.randn(N, K, device=dev()) / math.sqrt(K)).bfloat16()
     bias = torch.randn(N, device=dev())
     res = torch.randn(1, M, N, device=dev()).bfloat16()
-    stats = torch.full((M, N // 64, 2), float("nan"), device=dev())
+    stats = torch.full((M, N // 128, 2), float("nan"), device=dev())
     got = packing.linear_res_stats(x, w_nk, bias, res, stats)
     want = x.float()[0] @ w_nk.float().t() + bias + res.float()[0]
     assert rel_err(got[0], want) <= 2 ** -7
-    wc = want.view(M, N // 64, 64)
+    wc = want.view(M, N // 128, 128)
     assert torch.allclose(stats[..., 0], wc.sum(-1), rtol=1e-3, atol=2e-2)
     assert torch.allclose(stats[..., 1], (wc * wc).sum(-1), rtol=1e-3, atol=2e-2)
     again = torch.empty_like(stats)

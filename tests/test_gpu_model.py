@@ -154,19 +154,22 @@ def test_layernorm_folding_matches_unfolded_and_hf():
     x = hf_oracle.make_input("vit-b16-224", 3)
     want = hf_oracle.hf_forward(hf, x)
     xd = x.to(DEV, torch.bfloat16)
-    with torch.no_grad():
-        plain = model(xd).float().cpu()
-        vit_mod.set_layernorm_folding(True)
-        try:
-            folded = model(xd).float().cpu()
-            again = model(xd).float().cpu()
-        finally:
-            vit_mod.set_layernorm_folding(False)
-    assert torch.equal(folded, again)         # statistics are exchanged without atomics
-    for got in (folded, plain):
-        assert _cos(got, want) >= 0.999 and (got - want).abs().max().item() <= 0.15
-    assert _cos(folded, plain) >= 0.9995
-    assert (folded - want).abs().max().item() <= 1.5 * (plain - want).abs().max().item() + 0.02
+    results = {}
+    try:
+        with torch.no_grad():
+            for name, (fold, mlp) in {"plain": (False, False), "qkv": (True, False), "both": (True, True)}.items():
+                vit_mod.set_layernorm_folding(fold, mlp=mlp)
+                results[name] = model(xd).float().cpu()
+                assert torch.equal(results[name], model(xd).float().cpu())   # statistics are exchanged without atomics
+    finally:
+        vit_mod.set_layernorm_folding(True, mlp=True)     # the defaults
+    plain = results["plain"]
+    for name, got in results.items():
+        assert _cos(got, want) >= 0.999 and (got - want).abs().max().item() <= 0.15, name
+    for name in ("qkv", "both"):
+        folded = results[name]
+        assert _cos(folded, plain) >= 0.9995, name
+        assert (folded - want).abs().max().item() <= 1.5 * (plain - want).abs().max().item() + 0.02, name
 
 
 @pytest.mark.parametrize("arch", ["vit-l16-224", "vit-h14-224"])

@@ -20,7 +20,7 @@ def run(n):
     return s.elapsed_time(e) / n
 with torch.no_grad():
     for rep in range(3):
-        for fold in (False, True):
-            V.set_layernorm_folding(fold)
+        for fold, mlp in ((False, False), (True, False), (True, True)):
+            V.set_layernorm_folding(fold, mlp=mlp)
             run(5)
-            print(f"rep {rep} fold={fold}: {run(60):.3f} ms/forward", flush=True)
+            print(f"rep {rep} fold={fold} mlp={mlp}: {run(60):.3f} ms/forward", flush=True)

@@ -76,15 +76,20 @@ struct Gemm2Params {
   int reverse;                    // walk the row tiles from the last to the first (L2 reuse, see api.cu)
   const float* bias;
   // LayerNorm folded into the epilogue (EPI_LNF): out = rstd_m * acc + (-rstd_m * mean_m) * colsum_n + bias_n
-  // with (sum, sumsq) of the A row given as ln_parts partial pairs rowstats[(m*ln_parts + i)*2 .. +1]
+  // with (sum, sumsq) of the A row given as ln_parts = ln_dim / 128 partial pairs
+  // rowstats[(m*ln_parts + i)*2 .. +1]
   const float* rowstats;
   const float* colsum;
   float ln_inv_dim, ln_eps;
   int ln_parts;
-  // EPI_STATS: write (sum, sumsq) of every 64-column chunk of every output row to
-  // stats_out[(m * (N/64) + chunk) * 2 .. +1]: no atomics, so results are bit-reproducible
+  // EPI_STATS: write (sum, sumsq) of every 128-column group (one epilogue warp's share of a tile) of
+  // every output row to stats_out[(m * (N/128) + group) * 2 .. +1]: no atomics, so results are
+  // bit-reproducible
   float* stats_out;
   long long* dbg;   // optional per-CTA cycle counters (vt_debug_set_buffer); null in production
+  // Epilogue pacing (see the epilogue): cycles between the start slots of the tile's store bursts,
+  // 0 = off; pace_q = additional stagger between the four lane-quarter warps of a slot
+  int pace, pace_q;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -162,7 +167,11 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
 }
 
+#ifdef VT_GELU_AS   // A/B switch: the two-MUFU Abramowitz-Stegun form
 __device__ __forceinline__ float2 gelu_epi2(float2 x) { return gelu_erf_bf16_x2(x); }
+#else
+__device__ __forceinline__ float2 gelu_epi2(float2 x) { return gelu_erf_poly_x2(x); }
+#endif
 
 template <int EPI, typename Cfg>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -322,12 +331,54 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     int as = 0;
     uint32_t aphase = 0;
     uint32_t rphase = 0;
-    for (int t = first_tile; t < num_tiles; t += tile_step) {
+
+    // Per-column and per-row epilogue operands.  With 224 KB of the SM's 228 KB configured as shared
+    // memory there is practically no L1: every __ldg is an L2 round trip (~700 cycles under load),
+    // and loading the bias of each 32-column step at the step cost the plain epilogue 3300 cycles per
+    // tile, four fifths of it latency (tools/gemm_dbg.py).  So: lane l keeps the bias (and the folded
+    // LayerNorm's column sums) of columns 4l..4l+3 of this warp's 128 — ONE coalesced 16-byte load per
+    // tile — and the steps broadcast them with shuffles; those loads and the row statistics of the
+    // NEXT tile are issued before the current tile's staging buffers drain.
+    static_assert(kColsPerWarp == 128, "lane-owned bias layout: 32 lanes x 4 columns");
+    constexpr int kRsRegs = 5;                     // row statistics prefetched as up to 5 float4 (K <= 1280)
+    const bool rs_fast = (EPI & EPI_LNF) && (p.ln_parts % 2 == 0) && (p.ln_parts <= 2 * kRsRegs) &&
+                         (reinterpret_cast<uintptr_t>(p.rowstats) & 15) == 0;
+    float4 b4n = make_float4(0.f, 0.f, 0.f, 0.f), c4n = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 rsn[kRsRegs];
+#pragma unroll
+    for (int i = 0; i < kRsRegs; ++i) rsn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto tile_origin = [&](int t, int& row0, int& col0) {
       int m_blk = t / p.num_n_tiles;
       const int n_blk = t - m_blk * p.num_n_tiles;
       if (p.reverse) m_blk = p.num_m_tiles - 1 - m_blk;
-      const int row0 = m_blk * (2 * BM) + static_cast<int>(cta_rank) * BM + q * 32;
-      const int col0 = n_blk * BN + cgrp * kColsPerWarp;
+      row0 = m_blk * (2 * BM) + static_cast<int>(cta_rank) * BM + q * 32;
+      col0 = n_blk * BN + cgrp * kColsPerWarp;
+    };
+    auto prefetch_operands = [&](int t) {
+      int row0, col0;
+      tile_origin(t, row0, col0);
+      const int cb = col0 + 4 * lane;
+      const bool in = cb + 3 < p.N;              // N % 8 == 0: groups of 4 are all in or all out
+      b4n = (p.bias != nullptr && in) ? __ldg(reinterpret_cast<const float4*>(p.bias + cb))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (EPI & EPI_LNF) {
+        c4n = in ? __ldg(reinterpret_cast<const float4*>(p.colsum + cb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int row = row0 + lane;
+        if (rs_fast && row < p.M) {
+          const float4* parts =
+              reinterpret_cast<const float4*>(p.rowstats + static_cast<long long>(row) * p.ln_parts * 2);
+#pragma unroll
+          for (int i = 0; i < kRsRegs; ++i)
+            if (2 * i < p.ln_parts) rsn[i] = __ldg(parts + i);
+        }
+      }
+    };
+    if (first_tile < num_tiles) prefetch_operands(first_tile);
+
+    for (int t = first_tile; t < num_tiles; t += tile_step) {
+      int row0, col0;
+      tile_origin(t, row0, col0);
+      const float4 b4 = b4n, c4 = c4n;
 
       if (EPI & EPI_RES) {
         if (lane == 0) {
@@ -344,12 +395,25 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       if (EPI & EPI_LNF) {
         const int row = row0 + lane;
         if (row < p.M) {
-          const float2* parts = reinterpret_cast<const float2*>(p.rowstats) + static_cast<long long>(row) * p.ln_parts;
           float sx = 0.f, sq = 0.f;
-          for (int i = 0; i < p.ln_parts; ++i) {   // fixed order: deterministic
-            const float2 st = __ldg(parts + i);
-            sx += st.x;
-            sq += st.y;
+          if (rs_fast) {                            // fixed order: deterministic
+#pragma unroll
+            for (int i = 0; i < kRsRegs; ++i) {
+              if (2 * i < p.ln_parts) {
+                sx += rsn[i].x;
+                sq += rsn[i].y;
+                sx += rsn[i].z;
+                sq += rsn[i].w;
+              }
+            }
+          } else {
+            const float2* parts =
+                reinterpret_cast<const float2*>(p.rowstats) + static_cast<long long>(row) * p.ln_parts;
+            for (int i = 0; i < p.ln_parts; ++i) {
+              const float2 st = __ldg(parts + i);
+              sx += st.x;
+              sq += st.y;
+            }
           }
           const float mean = sx * p.ln_inv_dim;
           const float var = fmaxf(sq * p.ln_inv_dim - mean * mean, 0.f);
@@ -360,11 +424,22 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 
       long long w0 = 0;
       if (p.dbg) w0 = clock64();
-      mbar_wait(tfull_bar(as), aphase);
+      // Pacing.  All eight warps would otherwise read their accumulator quarter and push their chunk
+      // through the TMA at the same moment, twice per tile: the 32 KB store bursts collide with the
+      // operand loads on the SM's L2 port (which the mainloop alone already fills) and every tile loses
+      // 300-600 cycles (tools/gemm_dbg.py: a SLOWER epilogue made the same GEMM faster).  When the
+      // accumulator was not ready yet (the epilogue is ahead of the mainloop) chunk c of column group g
+      // therefore starts no earlier than slot (2c + g) after the accumulator arrived; a warp that
+      // found the accumulator waiting is behind and does not pace.
+      const bool ahead = !mbar_test_wait(tfull_bar(as), aphase);
+      if (ahead) mbar_wait(tfull_bar(as), aphase);
       if (p.dbg) { const long long w1 = clock64(); dbg_acc[0] += w1 - w0; w0 = w1; }
       tc_fence_after();
+      const bool paced = ahead && p.pace > 0;
+      const long long pace_t0 = paced ? clock64() + q * p.pace_q : 0;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + cgrp * kColsPerWarp;
 
+      float2 st_sum2 = make_float2(0.f, 0.f), st_sq2 = make_float2(0.f, 0.f);   // even / odd columns
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
         const int col = col0 + c * kChunkCols;
@@ -381,28 +456,35 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           __syncwarp();
         }
         if (EPI & EPI_RES) mbar_wait(res_bar(ew, c), rphase);
+        if (paced) {
+          const long long until = pace_t0 + static_cast<long long>(2 * c + cgrp) * p.pace;
+          while (clock64() < until) __nanosleep(32);
+        }
         uint8_t* rowp = stage_gen[c] + lane * 128;
-        float2 st_sum2 = make_float2(0.f, 0.f), st_sq2 = make_float2(0.f, 0.f);   // even / odd columns
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           uint32_t r[32];
           tmem_ld_32x32(t_addr + c * kChunkCols + hh * 32, r);
-          // bias for these 32 columns: issued before the TMEM wait so both latencies overlap
+          // bias (and folded-LayerNorm term) of these 32 columns, broadcast from the owning lanes
+          // while the TMEM load is in flight
           float4 bv[8];
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            const int cb = col + hh * 32 + 4 * g;
-            bv[g] = (p.bias != nullptr && cb + 3 < p.N)   // N % 8 == 0: groups of 4 are all in or all out
-                        ? __ldg(reinterpret_cast<const float4*>(p.bias + cb))
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int src = 16 * c + 8 * hh + g;
+            bv[g].x = __shfl_sync(0xffffffffu, b4.x, src);
+            bv[g].y = __shfl_sync(0xffffffffu, b4.y, src);
+            bv[g].z = __shfl_sync(0xffffffffu, b4.z, src);
+            bv[g].w = __shfl_sync(0xffffffffu, b4.w, src);
             if (EPI & EPI_LNF) {
-              if (cb + 3 < p.N) {
-                const float4 cs = __ldg(reinterpret_cast<const float4*>(p.colsum + cb));
-                const float2 lb = make_float2(ln_b, ln_b);
-                const float2 lo = __ffma2_rn(lb, make_float2(cs.x, cs.y), make_float2(bv[g].x, bv[g].y));
-                const float2 hi = __ffma2_rn(lb, make_float2(cs.z, cs.w), make_float2(bv[g].z, bv[g].w));
-                bv[g] = make_float4(lo.x, lo.y, hi.x, hi.y);
-              }
+              float4 cs;
+              cs.x = __shfl_sync(0xffffffffu, c4.x, src);
+              cs.y = __shfl_sync(0xffffffffu, c4.y, src);
+              cs.z = __shfl_sync(0xffffffffu, c4.z, src);
+              cs.w = __shfl_sync(0xffffffffu, c4.w, src);
+              const float2 lb = make_float2(ln_b, ln_b);
+              const float2 lo = __ffma2_rn(lb, make_float2(cs.x, cs.y), make_float2(bv[g].x, bv[g].y));
+              const float2 hi = __ffma2_rn(lb, make_float2(cs.z, cs.w), make_float2(bv[g].z, bv[g].w));
+              bv[g] = make_float4(lo.x, lo.y, hi.x, hi.y);
             }
           }
           tmem_ld_wait();
@@ -463,11 +545,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             *slot = o4;
           }
         }
-        if (EPI & EPI_STATS) {
+        if ((EPI & EPI_STATS) && c == kChunks - 1) {
           const int row = row0 + lane;
-          if (live && row < p.M) {
+          if (col0 < p.N && row < p.M) {          // N % 128 == 0: a warp's two chunks are both in or both out
             float2* dst = reinterpret_cast<float2*>(p.stats_out) +
-                          static_cast<long long>(row) * (p.N >> 6) + (col >> 6);
+                          static_cast<long long>(row) * (p.N >> 7) + (col0 >> 7);
             *dst = make_float2(st_sum2.x + st_sum2.y, st_sq2.x + st_sq2.y);
           }
         }
@@ -481,6 +563,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         }
       }
       if (p.dbg) { const long long w1 = clock64(); dbg_acc[1] += w1 - w0; w0 = w1; }
+      if (t + tile_step < num_tiles) prefetch_operands(t + tile_step);
       // staging buffers must be drained (read by the TMA engine) before the next tile reuses them
       if (lane == 0) tma_store_wait_read<0>();
       __syncwarp();
@@ -546,8 +629,8 @@ int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long l
   if (gelu && residual) return VT_ERR_UNSUPPORTED;
   if ((rowstats != nullptr) != (colsum != nullptr)) return VT_ERR_ARG;
   if (rowstats && (residual || stats_out || ln_dim <= 0)) return VT_ERR_UNSUPPORTED;
-  if (stats_out && (!residual || (N % 64))) return VT_ERR_UNSUPPORTED;
-  if (rowstats && (ln_dim % 64)) return VT_ERR_UNSUPPORTED;
+  if (stats_out && (!residual || (N % 128))) return VT_ERR_UNSUPPORTED;
+  if (rowstats && (ln_dim % 128)) return VT_ERR_UNSUPPORTED;
   if ((K % 8) || (lda % 8) || (ldb % 8) || (N % 8) || (ldo % 8) || (residual && (ldr % 8)))
     return VT_ERR_ALIGN;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bt) |
@@ -581,17 +664,36 @@ int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long l
   p.colsum = colsum;
   p.ln_inv_dim = ln_dim > 0 ? 1.0f / static_cast<float>(ln_dim) : 0.f;
   p.ln_eps = ln_eps;
-  p.ln_parts = ln_dim / 64;
+  p.ln_parts = ln_dim / 128;
   p.stats_out = stats_out;
   p.dbg = g_dbg_buffer;
-  // Shared-memory split per epilogue (see G2Cfg): GELU, LayerNorm-fold and short-K residual epilogues
-  // keep two staging buffers per warp, everything else takes the sixth operand stage.  VT_GEMM_STAGES=5|6 forces one.
+  // Slot spacing: 21 % of the ideal tile time (K blocks x 4 MMAs x 128 cycles), at most that of a
+  // K = 768 tile (1290 cycles: a K = 3072 tile gains nothing from wider slots), plus 5 % between the
+  // four lane-quarter warps of a slot.  Measured (tools/gemm_dbg.py, cycles per launch at C2):
+  // plain QKV 174.0k -> 157.9k, folded QKV 174.1k -> 159.3k, fc1 + GELU 230.7k -> 214.4k,
+  // out-proj + residual 71.6k -> 67.0k, fc2 212.3k -> 206.5k.  VT_GEMM_PACE / VT_GEMM_PACE_Q (permille)
+  // override; 0 switches pacing off.
+  static const int pace_pm = [] { const char* e = getenv("VT_GEMM_PACE"); return e ? atoi(e) : 210; }();
+  static const int pace_q_pm = [] { const char* e = getenv("VT_GEMM_PACE_Q"); return e ? atoi(e) : 50; }();
+  long long ideal = static_cast<long long>((K + BK - 1) / BK) * 512;
+  if (ideal > 6144) ideal = 6144;
+  p.pace = static_cast<int>(ideal * pace_pm / 1000);
+  p.pace_q = static_cast<int>(ideal * pace_q_pm / 1000);
+  // Shared-memory split per epilogue (see G2Cfg): GELU and short-K residual epilogues keep two staging
+  // buffers per warp, everything else (the LayerNorm fold included, now that its operands are
+  // prefetched: 7947 -> 7050 cycles per tile) takes the sixth operand stage.  VT_GEMM_STAGES=5|6 forces
+  // one for every launch, VT_LNF_STAGES=5|6 for the LayerNorm-fold launches only.
   static const int forced = [] {
     const char* e = getenv("VT_GEMM_STAGES");
     return (e && (e[0] == '5' || e[0] == '6')) ? (e[0] - '0') : 0;
   }();
-  const bool epilogue_heavy = gelu || rowstats != nullptr || (residual && K < 2048);
-  const bool deep = forced ? (forced == 6) : !epilogue_heavy;
+  static const int forced_lnf = [] {
+    const char* e = getenv("VT_LNF_STAGES");
+    return (e && (e[0] == '5' || e[0] == '6')) ? (e[0] - '0') : 0;
+  }();
+  const bool epilogue_heavy = gelu || (residual && K < 2048);
+  bool deep = forced ? (forced == 6) : !epilogue_heavy;
+  if (rowstats && forced_lnf) deep = (forced_lnf == 6);
 #define VT_G2_LAUNCH(E) (deep ? launch2<E, G2Deep>(ta, tb, to, tr, p, stream) : launch2<E, G2Wide>(ta, tb, to, tr, p, stream))
   if (rowstats) return gelu ? VT_G2_LAUNCH(EPI_LNF | EPI_GELU) : VT_G2_LAUNCH(EPI_LNF);
   if (gelu) return VT_G2_LAUNCH(EPI_GELU);

@@ -101,8 +101,10 @@ def pack_block_folded(block) -> SimpleNamespace:
     NOT folded: the extra per-element FMAs land in the GELU epilogue, which already paces that GEMM —
     measured +35 us per layer against the 31 us LayerNorm kernel it would remove.)"""
     att = block.attention.packed()
+    mlp = block.packed()
     wqkv, bqkv, cqkv = _fold_layernorm(att.wqkv, att.bqkv, block.layernorm_before)
-    return SimpleNamespace(wqkv=wqkv, bqkv=bqkv, cqkv=cqkv)
+    w1, b1, c1 = _fold_layernorm(mlp.w1, mlp.b1, block.layernorm_after)
+    return SimpleNamespace(wqkv=wqkv, bqkv=bqkv, cqkv=cqkv, w1=w1, b1=b1, c1=c1)
 
 
 def pack_embeddings(emb) -> SimpleNamespace:
@@ -182,15 +184,18 @@ def patch_embed_u8(emb, x: torch.Tensor, image_mean, image_std, rescale_factor: 
     return out
 
 
+STATS_COLS = 128   # columns per (sum, sumsq) partial of the row statistics (VT_LN_STATS_COLS in include/vitb200.h)
+
+
 def folding_supported(x: torch.Tensor, dim: int, mlp_dim: int) -> bool:
     """LayerNorm folding runs on the bf16 tensor-core GEMM only."""
-    return x.is_cuda and x.dtype == torch.bfloat16 and dim % 64 == 0 and mlp_dim % 8 == 0
+    return x.is_cuda and x.dtype == torch.bfloat16 and dim % STATS_COLS == 0 and mlp_dim % 8 == 0
 
 
 def linear_ln(x: torch.Tensor, w_fold: torch.Tensor, b_fold: torch.Tensor, colsum: torch.Tensor,
               rowstats: torch.Tensor, eps: float, gelu: bool = False) -> torch.Tensor:
     """out = act(LN(x) @ W^T + b) computed as a GEMM on the un-normalised x with the normalisation
-    applied per row in the epilogue; ``rowstats`` is the (M, K/64, 2) fp32 table of per-64-column
+    applied per row in the epilogue; ``rowstats`` is the (M, K/128, 2) fp32 table of per-128-column
     (sum, sumsq) partials of x's rows written by ``linear_res_stats``."""
     B, N, K = x.shape
     n_out = w_fold.shape[0]
@@ -203,8 +208,8 @@ def linear_ln(x: torch.Tensor, w_fold: torch.Tensor, b_fold: torch.Tensor, colsu
 
 def linear_res_stats(x: torch.Tensor, w_nk: torch.Tensor, bias32: torch.Tensor, residual: torch.Tensor,
                      stats_out: torch.Tensor) -> torch.Tensor:
-    """out = x @ W^T + b + residual, also writing every output row's per-64-column (sum, sumsq) partials
-    into the (M, N/64, 2) fp32 ``stats_out`` for the LayerNorm folded into the next GEMM."""
+    """out = x @ W^T + b + residual, also writing every output row's per-128-column (sum, sumsq) partials
+    into the (M, N/128, 2) fp32 ``stats_out`` for the LayerNorm folded into the next GEMM."""
     B, N, K = x.shape
     n_out = w_nk.shape[0]
     out = torch.empty((B, N, n_out), device=x.device, dtype=x.dtype)

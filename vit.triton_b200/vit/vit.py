@@ -43,6 +43,7 @@ _FUSED = True
 # +10 us fc2), but under the sustained power cap the forward is 1.3-2.3 % faster (tools/fold_ab.py:
 # 9.55 -> 9.33, 9.64 -> 9.52, 9.62 -> 9.45 ms): 12 launches and 1.9 GB of activation traffic less.
 _FOLD_LN = True
+_FOLD_LN_MLP = True    # layernorm_after -> fc1 fold (statistics from the out-proj epilogue), see set_layernorm_folding
 
 
 def set_fused(enabled: bool) -> None:
@@ -56,11 +57,12 @@ def fused_enabled() -> bool:
     return _FUSED
 
 
-def set_layernorm_folding(enabled: bool) -> None:
+def set_layernorm_folding(enabled: bool, mlp: bool = True) -> None:
     """Toggle folding of layernorm_before into the QKV GEMM epilogue (default ON, see the note at
     _FOLD_LN; only affects the fused bf16 path).  Off = 7 launches per block instead of 6."""
-    global _FOLD_LN
+    global _FOLD_LN, _FOLD_LN_MLP
     _FOLD_LN = bool(enabled)
+    _FOLD_LN_MLP = bool(enabled and mlp)
 
 
 class LinearWithBias(nn.Module):
@@ -173,7 +175,7 @@ class Transformer(packing.PackedMixin, nn.Module):
     def forward_folded(self, x: torch.Tensor, ln1_stats: Optional[torch.Tensor]):
         """Block forward with layernorm_before folded into the QKV GEMM (bf16 only).
 
-        ``ln1_stats``: (M, D/64, 2) fp32 per-64-column (sum, sumsq) partials of x's rows, written by the
+        ``ln1_stats``: (M, D/128, 2) fp32 per-128-column (sum, sumsq) partials of x's rows, written by the
         previous block's last GEMM (None for the first block: layernorm_before then runs as a
         kernel).  Returns (output, statistics of the output rows).  6 launches instead of 7."""
         att = self.attention.packed()
@@ -185,9 +187,16 @@ class Transformer(packing.PackedMixin, nn.Module):
             pk = self.packed("folded")
             qkv = packing.linear_ln(x, pk.wqkv, pk.bqkv, pk.cqkv, ln1_stats, self.layernorm_before.eps)
         ctx = flash_attention(qkv, self.num_heads, 1.0 / math.sqrt(self.d_out))
-        res = packing.linear(ctx, att.wo, att.bo, residual=x)
-        mid = packing.linear(self.layernorm_after(res), mlp.w1, mlp.b1, gelu=True)
-        stats = torch.empty((x.shape[0] * x.shape[1], self.d_in // 64, 2), device=x.device, dtype=torch.float32)
+        if _FOLD_LN_MLP:
+            pk = self.packed("folded")
+            stats2 = torch.empty((x.shape[0] * x.shape[1], self.d_in // packing.STATS_COLS, 2), device=x.device,
+                                 dtype=torch.float32)
+            res = packing.linear_res_stats(ctx, att.wo, att.bo, x, stats2)
+            mid = packing.linear_ln(res, pk.w1, pk.b1, pk.c1, stats2, self.layernorm_after.eps, gelu=True)
+        else:
+            res = packing.linear(ctx, att.wo, att.bo, residual=x)
+            mid = packing.linear(self.layernorm_after(res), mlp.w1, mlp.b1, gelu=True)
+        stats = torch.empty((x.shape[0] * x.shape[1], self.d_in // packing.STATS_COLS, 2), device=x.device, dtype=torch.float32)
         out = packing.linear_res_stats(mid, mlp.w2, mlp.b2, res, stats)
         return out, stats
 
