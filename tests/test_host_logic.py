@@ -158,3 +158,25 @@ def test_data_parallel_gather_gloo_world2(tmp_path, total):
         rows = torch.load(tmp_path / f"rows{r}.pt")
         lo0, hi0 = shard_bounds(total, world, 0)
         assert torch.equal(rows[:hi0], torch.zeros(hi0, 2)) and torch.equal(rows[hi0:], torch.ones(total - hi0, 2))
+
+
+def test_gelu_polynomial_restatement_matches_exact_erf():
+    """The fc1 epilogue's GELU (csrc/common.cuh: gelu_erf_poly_x2) restated in fp32 numpy:
+    gelu(x) = relu(x) - 0.5|x| * 2^P(|x|), P a degree-5 polynomial for log2(erfc(a/sqrt(2))).
+    Must stay within 1e-6 absolute of the exact-erf GELU the reference computes
+    (vit/kernels/activations.py:19-20) and underflow cleanly for large |x|."""
+    import numpy as np
+    coef = [np.float32(c) for c in (-0.00048810223, 0.0071987188, -0.052146632, -0.45959586, -1.1510005)]
+    x = np.concatenate([np.linspace(-12, 12, 200001), [-1e4, -40.0, 0.0, 40.0, 1e4]]).astype(np.float32)
+    a = np.abs(x)
+    p = coef[0] * a + coef[1]
+    for c in coef[2:]:
+        p = p * a + c
+    p = p * a
+    assert (p <= 0).all()                                   # the exponential can never overflow
+    with np.errstate(over="ignore", under="ignore"):
+        e = np.exp2(p.astype(np.float64))
+    got = np.maximum(x, 0).astype(np.float64) - 0.5 * a.astype(np.float64) * e
+    want = torch.nn.functional.gelu(torch.from_numpy(x).double()).numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got - want).max() <= 1e-6
