@@ -70,6 +70,8 @@ int vt_gemm_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, void* 
  *     (summed in index order: bit-reproducible); ln_dim % 128 == 0; Bt must carry gamma
  *     (Bt[n,k] = W[n,k] * gamma[k]), bias must carry beta (bias[n] + sum_k beta[k] W[n,k]) and
  *     colsum[n] = sum_k Bt[n,k]:   out = rstd_m * acc - rstd_m * mean_m * colsum_n + bias_n  (then GELU).
+ *     colsum == NULL: the rows of Bt sum to zero (Bt[n,k] = W[n,k]*gamma[k] - mean_k(W[n,k]*gamma[k])), the
+ *     mean term is then part of acc and   out = rstd_m * acc + bias_n.
  *   stats_out != NULL (needs residual, N % 128 == 0): writes the (sum, sumsq) of every 128-column group
  *     of every output row to stats_out[(m*(N/128) + group)*2 .. +1] — the rowstats layout above.
  * Replaces layernorm_triton (vit/kernels/layernorm.py:90-127) + matmul_triton for the

@@ -374,7 +374,8 @@ def test_pool_cls():
 # ------------------------------------------------------------------------------- LayerNorm folded into the GEMM
 @pytest.mark.parametrize("M,K,N", [(197 * 5, 768, 2304), (300, 128, 512), (129, 1280, 264), (260, 384, 640), (70, 1536, 256)])
 @pytest.mark.parametrize("gelu", [False, True])
-def test_gemm_layernorm_fold(M, K, N, gelu):
+@pytest.mark.parametrize("zero_sum", [False, True])
+def test_gemm_layernorm_fold(M, K, N, gelu, zero_sum):
     """vt_gemm_bf16_ln == dense(LayerNorm(x)) with the normalisation applied in the epilogue."""
     from vit import packing
     x = (2.0 * torch.randn(1, M, K, device=dev()) + 0.7).bfloat16()
@@ -384,7 +385,12 @@ def test_gemm_layernorm_fold(M, K, N, gelu):
         ln.bias.copy_(0.2 * torch.randn(K, device=dev()))
     w_nk = (torch.randn(N, K, device=dev()) / math.sqrt(K)).bfloat16()
     bias = torch.randn(N, device=dev())
-    w_fold, b_fold, colsum = packing._fold_layernorm(w_nk, bias, ln)
+    if zero_sum:      # mean term inside the weights (rows sum to zero), no column-sum operand
+        w_fold, b_fold = packing._fold_layernorm_zero_sum(w_nk, bias, ln)
+        colsum = None
+        assert w_fold.double().sum(dim=1).abs().max().item() <= 2e-3 * w_fold.float().abs().mean().item()
+    else:
+        w_fold, b_fold, colsum = packing._fold_layernorm(w_nk, bias, ln)
     xf = x.float()[0]
     xc = xf.view(M, K // 128, 128)
     stats = torch.stack([xc.sum(-1), (xc * xc).sum(-1)], dim=2).contiguous()      # (M, K/128, 2) partials

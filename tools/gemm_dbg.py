@@ -9,7 +9,8 @@ lib.vt_debug_set_buffer.argtypes = [ctypes.c_void_p]
 lib.vt_debug_set_buffer.restype = None
 M = 256 * 197
 dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
-CASES = ((768, 2304, 0, False, ""), (768, 2304, 0, False, "lnf"), (768, 3072, 1, False, ""), (768, 3072, 1, False, "lnf"),
+CASES = ((768, 2304, 0, False, ""), (768, 2304, 0, False, "lnf"), (768, 2304, 0, False, "lnz"), (768, 3072, 1, False, ""),
+         (768, 3072, 1, False, "lnf"), (768, 3072, 1, False, "lnz"),
          (768, 3072, 0, False, ""), (768, 768, 0, True, ""), (768, 768, 0, True, "stats"), (3072, 768, 0, True, ""),
          (3072, 768, 0, True, "stats"))
 for (K, N, act, res, mode) in CASES:
@@ -22,9 +23,10 @@ for (K, N, act, res, mode) in CASES:
     colsum = torch.randn(N, device="cuda")
     stats_out = torch.empty(M, N // 128, 2, device="cuda")
     def run():
-        if mode == "lnf":
+        if mode in ("lnf", "lnz"):
             _lib.call("vt_gemm_bf16_ln", x.data_ptr(), K, w.data_ptr(), K, out.data_ptr(), N, bias.data_ptr(), None, 0,
-                      M, N, K, act, rowstats.data_ptr(), colsum.data_ptr(), K, 1e-12, None, _lib.stream_ptr(x))
+                      M, N, K, act, rowstats.data_ptr(), colsum.data_ptr() if mode == "lnf" else None, K, 1e-12, None,
+                      _lib.stream_ptr(x))
         elif mode == "stats":
             _lib.call("vt_gemm_bf16_ln", x.data_ptr(), K, w.data_ptr(), K, out.data_ptr(), N, bias.data_ptr(), r.data_ptr(), N,
                       M, N, K, 0, None, None, 0, 0.0, stats_out.data_ptr(), _lib.stream_ptr(x))

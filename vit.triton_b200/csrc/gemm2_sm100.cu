@@ -68,7 +68,9 @@ using G2Deep = G2Cfg<6, 1>;
 using G2Wide = G2Cfg<5, 2>;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;             // clears the CTA-rank bit of a cluster smem address
 
-enum : int { EPI_GELU = 1, EPI_RES = 2, EPI_LNF = 4, EPI_STATS = 8 };
+// EPI_NOCS (with EPI_LNF): the folded weights have zero-sum rows (packing._fold_layernorm_zero_sum), so the
+// mean term is already inside the accumulator and the epilogue needs no column sums.
+enum : int { EPI_GELU = 1, EPI_RES = 2, EPI_LNF = 4, EPI_STATS = 8, EPI_NOCS = 16 };
 
 struct Gemm2Params {
   int M, N, K;
@@ -362,7 +364,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       b4n = (p.bias != nullptr && in) ? __ldg(reinterpret_cast<const float4*>(p.bias + cb))
                                       : make_float4(0.f, 0.f, 0.f, 0.f);
       if (EPI & EPI_LNF) {
-        c4n = in ? __ldg(reinterpret_cast<const float4*>(p.colsum + cb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!(EPI & EPI_NOCS))
+          c4n = in ? __ldg(reinterpret_cast<const float4*>(p.colsum + cb)) : make_float4(0.f, 0.f, 0.f, 0.f);
         const int row = row0 + lane;
         if (rs_fast && row < p.M) {
           const float4* parts =
@@ -475,7 +478,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             bv[g].y = __shfl_sync(0xffffffffu, b4.y, src);
             bv[g].z = __shfl_sync(0xffffffffu, b4.z, src);
             bv[g].w = __shfl_sync(0xffffffffu, b4.w, src);
-            if (EPI & EPI_LNF) {
+            if ((EPI & EPI_LNF) && !(EPI & EPI_NOCS)) {
               float4 cs;
               cs.x = __shfl_sync(0xffffffffu, c4.x, src);
               cs.y = __shfl_sync(0xffffffffu, c4.y, src);
@@ -619,15 +622,15 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
 void gemm2_set_debug_buffer(void* ptr) { g_dbg_buffer = static_cast<long long*>(ptr); }
 
 // bf16 in / bf16 out 2-CTA GEMM.  Same argument meaning as gemm_bf16_tcgen05 (out dtype fixed), plus
-// the optional LayerNorm fold (rowstats + colsum: the A operand is the un-normalised activation and
-// the weights carry gamma) and the optional output row statistics for the next fold.
+// the optional LayerNorm fold (rowstats [+ colsum]: the A operand is the un-normalised activation and
+// the weights carry gamma; without colsum their rows must sum to zero) and the optional output row statistics for the next fold.
 int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long ldb, void* out,
                        long long ldo, const float* bias, const void* residual, long long ldr, int M,
                        int N, int K, int gelu, const float* rowstats, const float* colsum, int ln_dim,
                        float ln_eps, float* stats_out, int reverse, cudaStream_t stream) {
   if (!A || !Bt || !out || M <= 0 || N <= 0 || K <= 0) return VT_ERR_ARG;
   if (gelu && residual) return VT_ERR_UNSUPPORTED;
-  if ((rowstats != nullptr) != (colsum != nullptr)) return VT_ERR_ARG;
+  if (colsum && !rowstats) return VT_ERR_ARG;
   if (rowstats && (residual || stats_out || ln_dim <= 0)) return VT_ERR_UNSUPPORTED;
   if (stats_out && (!residual || (N % 128))) return VT_ERR_UNSUPPORTED;
   if (rowstats && (ln_dim % 128)) return VT_ERR_UNSUPPORTED;
@@ -695,6 +698,7 @@ int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long l
   bool deep = forced ? (forced == 6) : !epilogue_heavy;
   if (rowstats && forced_lnf) deep = (forced_lnf == 6);
 #define VT_G2_LAUNCH(E) (deep ? launch2<E, G2Deep>(ta, tb, to, tr, p, stream) : launch2<E, G2Wide>(ta, tb, to, tr, p, stream))
+  if (rowstats && !colsum) return gelu ? VT_G2_LAUNCH(EPI_LNF | EPI_NOCS | EPI_GELU) : VT_G2_LAUNCH(EPI_LNF | EPI_NOCS);
   if (rowstats) return gelu ? VT_G2_LAUNCH(EPI_LNF | EPI_GELU) : VT_G2_LAUNCH(EPI_LNF);
   if (gelu) return VT_G2_LAUNCH(EPI_GELU);
   if (residual) return stats_out ? VT_G2_LAUNCH(EPI_RES | EPI_STATS) : VT_G2_LAUNCH(EPI_RES);

@@ -96,15 +96,50 @@ def _fold_layernorm(w_nk: torch.Tensor, bias32: torch.Tensor, ln) -> tuple:
     return w_fold, b_fold, colsum
 
 
+def _fold_layernorm_zero_sum(w_nk: torch.Tensor, bias32: torch.Tensor, ln, passes: int = 6) -> tuple:
+    """The same fold with the mean term moved INTO the weights: every row of W * gamma is shifted by
+    its own mean, so that  x @ W'^T = x @ (W * gamma)^T - mean(x) * colsum(W * gamma)  comes out of the
+    GEMM itself and the epilogue is just  rstd * acc + (b + W @ beta)  — no column-sum operand, one FMA
+    per element less.  What is left of the mean term is  rstd * mean * sum_k(rounded W'[n, k]); the
+    rounding residue of each row (~3e-3 after plain bf16 rounding of a 768-wide row) is cancelled by
+    rounding a few elements the OTHER way — those closest to a rounding tie first, so the move costs
+    almost nothing in accuracy — which leaves |sum_k W'| at the 1e-6 level.  Returns (W', b + W @ beta)."""
+    w32 = w_nk.float()
+    wg = w32 * ln.weight.detach().float()[None, :]
+    b_fold = (bias32 + w32 @ ln.bias.detach().float()).contiguous()
+    exact = wg - wg.mean(dim=1, keepdim=True)
+    wz = exact.to(w_nk.dtype)
+    if w_nk.dtype == torch.bfloat16:
+        moved = torch.zeros(wz.shape, dtype=torch.bool, device=wz.device)   # every element moves at most once
+        for _ in range(passes):
+            f = wz.float()
+            resid = f.double().sum(dim=1).float()[:, None]                   # (N, 1): what has to go
+            ulp = torch.exp2(torch.floor(torch.log2(f.abs().clamp_min(1e-30))) - 7.0)
+            err = exact - f                                                  # rounding error so far
+            ok = ~moved & (ulp <= resid.abs())
+            # added squared error per unit of residue removed: small for elements that were rounded
+            # the wrong way by almost half an ulp, large for those rounded the right way already
+            helps = err * resid < 0
+            price = torch.where(ok, ulp + torch.where(helps, -2.0, 2.0) * err.abs(), torch.full_like(ulp, float("inf")))
+            order = price.argsort(dim=1)
+            step = torch.where(ok, ulp, torch.zeros_like(ulp)).gather(1, order)
+            take = (step.cumsum(dim=1) <= resid.abs()) & (step > 0)          # cheapest prefix that fits
+            delta = torch.zeros_like(f).scatter(1, order, torch.where(take, step, torch.zeros_like(step)))
+            f = f - torch.sign(resid) * delta                                # exact: one ulp of each element
+            moved |= delta > 0
+            wz = f.to(torch.bfloat16)
+    return wz.contiguous(), b_fold
+
+
 def pack_block_folded(block) -> SimpleNamespace:
     """layernorm_before folded into the QKV weights of one encoder block.  (layernorm_after -> fc1 is
     NOT folded: the extra per-element FMAs land in the GELU epilogue, which already paces that GEMM —
     measured +35 us per layer against the 31 us LayerNorm kernel it would remove.)"""
     att = block.attention.packed()
     mlp = block.packed()
-    wqkv, bqkv, cqkv = _fold_layernorm(att.wqkv, att.bqkv, block.layernorm_before)
-    w1, b1, c1 = _fold_layernorm(mlp.w1, mlp.b1, block.layernorm_after)
-    return SimpleNamespace(wqkv=wqkv, bqkv=bqkv, cqkv=cqkv, w1=w1, b1=b1, c1=c1)
+    wqkv, bqkv = _fold_layernorm_zero_sum(att.wqkv, att.bqkv, block.layernorm_before)
+    w1, b1 = _fold_layernorm_zero_sum(mlp.w1, mlp.b1, block.layernorm_after)
+    return SimpleNamespace(wqkv=wqkv, bqkv=bqkv, cqkv=None, w1=w1, b1=b1, c1=None)
 
 
 def pack_embeddings(emb) -> SimpleNamespace:
@@ -192,7 +227,7 @@ def folding_supported(x: torch.Tensor, dim: int, mlp_dim: int) -> bool:
     return x.is_cuda and x.dtype == torch.bfloat16 and dim % STATS_COLS == 0 and mlp_dim % 8 == 0
 
 
-def linear_ln(x: torch.Tensor, w_fold: torch.Tensor, b_fold: torch.Tensor, colsum: torch.Tensor,
+def linear_ln(x: torch.Tensor, w_fold: torch.Tensor, b_fold: torch.Tensor, colsum: Optional[torch.Tensor],
               rowstats: torch.Tensor, eps: float, gelu: bool = False) -> torch.Tensor:
     """out = act(LN(x) @ W^T + b) computed as a GEMM on the un-normalised x with the normalisation
     applied per row in the epilogue; ``rowstats`` is the (M, K/128, 2) fp32 table of per-128-column
@@ -202,7 +237,7 @@ def linear_ln(x: torch.Tensor, w_fold: torch.Tensor, b_fold: torch.Tensor, colsu
     out = torch.empty((B, N, n_out), device=x.device, dtype=x.dtype)
     _lib.call("vt_gemm_bf16_ln", x.data_ptr(), K, w_fold.data_ptr(), K, out.data_ptr(), n_out,
               b_fold.data_ptr(), None, 0, B * N, n_out, K, 1 if gelu else 0, rowstats.data_ptr(),
-              colsum.data_ptr(), K, float(eps), None, _lib.stream_ptr(x))
+              _lib.ptr(colsum), K, float(eps), None, _lib.stream_ptr(x))
     return out
 
 
