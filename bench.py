@@ -405,7 +405,8 @@ def main():
         "config": {"workload": desc, "arch": arch, "per_gpu_batch": batch, "global_batch": global_batch,
                    "tokens": N_tok, "parallelism": f"dp{world}" if world > 1 else "single",
                    "l2": f"{n_rot} distinct input batches rotated; per-step activation footprint > L2",
-                   "weights": "random-init (trunc-normal 0.02), replicated"},
+                   "weights": "random-init (trunc-normal 0.02), replicated",
+                   "gather": ("pooled CLS embeddings, " + dp.gather_impl) if world > 1 else "none (one GPU)"},
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": "img/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": host_inputs[0].numel() * 2 * world,

@@ -1,0 +1,53 @@
+"""Worker of test_peer_gather_matches_nccl_world2 / tools: run under torchrun or mp.spawn with NCCL.
+
+Every rank builds the same tiny VIT, runs DataParallelVIT twice per step — through the fused
+pool + peer-store kernel (vt_pool_cls_allgather over symmetric memory) and through NCCL — and
+requires bit equality, for several steps (the flag counters and the buffer parity advance)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, "vit.triton_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch
+import torch.distributed as dist
+
+
+def run(rank: int, world: int, port: int, steps: int = 5) -> None:
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from vit import configs
+        from vit.parallel import DataParallelVIT
+        from vit.vit import VIT
+        torch.manual_seed(0)
+        model = VIT(**configs.vit_kwargs("tiny-b")).to("cuda", torch.bfloat16)
+        with torch.no_grad():
+            for p_ in model.parameters():
+                p_.copy_(torch.randn_like(p_) * 0.05)
+        fused = DataParallelVIT(model, peer_gather=True)
+        plain = DataParallelVIT(model, peer_gather=False)
+        size = configs.ARCHS["tiny-b"]["image_size"]
+        with torch.no_grad():
+            for step in range(steps):
+                g = torch.Generator(device="cuda").manual_seed(100 * step + rank)
+                x = torch.randn(6, 3, size, size, device="cuda", generator=g).bfloat16()
+                a = fused(x).clone()
+                b = plain(x)
+                assert fused.gather_impl == "peer-store kernel" and plain.gather_impl == "torch.distributed"
+                assert a.shape == b.shape == (6 * world, b.shape[1])
+                assert torch.equal(a, b), f"rank {rank} step {step}: peer-store gather differs from NCCL"
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            print("peer gather == nccl gather on", world, "ranks,", steps, "steps", flush=True)
+    finally:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    run(int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("MASTER_PORT", "29511")))

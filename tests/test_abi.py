@@ -9,7 +9,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "vitb200.h")
 
-_CTYPE = {"int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "float": ctypes.c_float}
+_CTYPE = {"int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "float": ctypes.c_float, "uint32_t": ctypes.c_uint32}
 
 
 def _declarations():
@@ -32,7 +32,7 @@ def _lib():
 def test_header_declares_expected_entry_points():
     names = set(_declarations())
     assert {"vt_layernorm", "vt_add", "vt_softmax", "vt_gemm_bf16", "vt_gemm_strided", "vt_flash_attn",
-            "vt_gemm_bf16_ln", "vt_patch_embed", "vt_patching", "vt_embed_finalize", "vt_conv2d", "vt_pool_cls", "vt_version",
+            "vt_gemm_bf16_ln", "vt_patch_embed", "vt_patching", "vt_embed_finalize", "vt_conv2d", "vt_pool_cls", "vt_pool_cls_allgather", "vt_version",
             "vt_status_string"} == names
 
 

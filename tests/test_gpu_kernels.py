@@ -418,3 +418,30 @@ def test_gemm_row_stats_output():
     again = torch.empty_like(stats)
     packing.linear_res_stats(x, w_nk, bias, res, again)
     assert torch.equal(stats, again)          # no atomics: bit-reproducible
+
+
+# ------------------------------------------------------------------------------- pool + peer all-gather (K7)
+def test_pool_cls_allgather_single_rank_protocol():
+    """vt_pool_cls_allgather with world = 1 (the rank is its own peer): rows land in the buffer of the
+    epoch's parity, the flag counter advances by blocks-per-peer each step, repeated steps do not hang."""
+    import ctypes
+    from vit.kernels import _lib
+    B, N, D = 37, 5, 768
+    flags = torch.zeros(1, dtype=torch.int32, device=dev())
+    bufs = torch.full((2, B, D), float("nan"), device=dev(), dtype=torch.bfloat16)
+    flag_tab = (ctypes.c_void_p * 1)(flags.data_ptr())
+    seen = []
+    for epoch in (1, 2, 3):
+        x = torch.randn(B, N, D, device=dev()).bfloat16()
+        out_tab = (ctypes.c_void_p * 1)(bufs[epoch & 1].data_ptr())
+        _lib.call("vt_pool_cls_allgather", x.data_ptr(), B, D, x.stride(0), _lib.VT_BF16,
+                  ctypes.cast(out_tab, ctypes.c_void_p), ctypes.cast(flag_tab, ctypes.c_void_p), 0, 1, epoch,
+                  _lib.stream_ptr(x))
+        torch.cuda.synchronize()
+        assert torch.equal(bufs[epoch & 1], x[:, 0, :])
+        seen.append(int(flags.item()))
+    assert seen[1] - seen[0] == seen[0] and seen[2] - seen[1] == seen[0] and seen[0] >= 1
+    with pytest.raises(_lib.KernelError):      # epoch 0 is reserved (flags start at zero)
+        _lib.call("vt_pool_cls_allgather", x.data_ptr(), B, D, x.stride(0), _lib.VT_BF16,
+                  ctypes.cast(out_tab, ctypes.c_void_p), ctypes.cast(flag_tab, ctypes.c_void_p), 0, 1, 0,
+                  _lib.stream_ptr(x))

@@ -227,3 +227,18 @@ def test_pooler_head_matches_hf_pooler():
             got = model.pooler_output(x.to(DEV, dtype)).float().cpu()
         assert got.shape == want.shape
         assert (got - want).abs().max().item() <= tol, f"{dtype}: max-abs {(got - want).abs().max().item()}"
+
+
+def test_peer_gather_matches_nccl_world2():
+    """Two ranks on two GPUs: the fused pool + peer-store gather kernel returns the same bits as
+    vt_pool_cls + NCCL all-gather, step after step (tests/peer_gather_worker.py)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import socket
+    import torch.multiprocessing as mp
+    import peer_gather_worker
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(peer_gather_worker.run, args=(2, port), nprocs=2, join=True)

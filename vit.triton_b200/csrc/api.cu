@@ -12,6 +12,8 @@ int layernorm_rows(const void*, const void*, const void*, void*, long long, int,
 int add_elementwise(const void*, const void*, void*, long long, int, cudaStream_t);
 int softmax_rows(const void*, void*, long long, int, long long, int, cudaStream_t);
 int pool_cls(const void*, void*, int, int, long long, int, cudaStream_t);
+int pool_cls_allgather(const void*, int, int, long long, int, void* const*, unsigned int* const*, int, int,
+                       unsigned int, cudaStream_t);
 int gemm_bf16_tcgen05(const void*, long long, const void*, long long, void*, long long, int,
                       const float*, const void*, long long, int, int, int, int, cudaStream_t);
 int gemm2_bf16_tcgen05(const void*, long long, const void*, long long, void*, long long, const float*,
@@ -200,6 +202,14 @@ int vt_conv2d(const void* input, const void* weight, const void* bias, void* out
 int vt_pool_cls(const void* x, void* out, int32_t B, int32_t D, int64_t batch_stride, int32_t dtype,
                 void* stream) {
   return vt::pool_cls(x, out, B, D, batch_stride, dtype, S(stream));
+}
+
+int vt_pool_cls_allgather(const void* x, int32_t B, int32_t D, int64_t batch_stride, int32_t dtype,
+                          void* const* peer_out, uint32_t* const* peer_flags, int32_t rank, int32_t world,
+                          uint32_t epoch, void* stream) {
+  return vt::pool_cls_allgather(x, B, D, batch_stride, dtype, peer_out,
+                                reinterpret_cast<unsigned int* const*>(peer_flags), rank, world, epoch,
+                                S(stream));
 }
 
 }  // extern "C"

@@ -369,7 +369,92 @@ __global__ void pool_cls_kernel(const T* __restrict__ x, T* __restrict__ out, in
   out[i] = x[b * batch_stride + c];
 }
 
+// ------------------------------------------------------------------------------------------
+// pool + all-gather over peer memory (K7): every rank stores the CLS rows of its images straight into
+// the gather buffer of every peer (NVLink P2P stores, 16 bytes per thread), then raises a counter in
+// that peer's flag array and waits until all peers have raised the counters in its own.  One kernel,
+// no NCCL call: the transfer is 393 KB per rank at C2, i.e. latency-bound, and the kernel saves the
+// separate pool launch, the NCCL launch and its internal synchronisation.
+//
+// Protocol (per step, epoch e = 1, 2, ...; flags are monotonic counters, never reset):
+//   writer block (p, j) of rank r: copy its slice of rows to peer p, __syncthreads, thread 0:
+//       fence.sys + red.release.sys.add  flags_p[r] += 1
+//   reader: thread 0 of block (p, 0) spins (ld.acquire.sys) until flags_self[p] >= e * blocks_per_peer.
+// The gather buffers are double-buffered by the parity of e on the host side: a peer can only be one
+// epoch ahead (it waited for this rank's flag of epoch e before starting e + 1), so the buffer of
+// epoch e - 1, which this rank's stream may still be reading, is never written.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+struct PeerTable {
+  void* out[kMaxPeers];            // gather buffer of every rank (this epoch's), (world * batch, dim)
+  unsigned int* flags[kMaxPeers];  // flag array of every rank, [world] counters
+};
+
+__global__ void __launch_bounds__(512)
+pool_cls_allgather_kernel(const uint4* __restrict__ x, long long batch_stride_v, int batch, int dim_v,
+                          PeerTable peers, int rank, int world, int blocks_per_peer, unsigned int epoch,
+                          long long out_row0_v) {
+  const int p = blockIdx.x / blocks_per_peer;      // destination rank
+  const int j = blockIdx.x - p * blocks_per_peer;
+  uint4* dst = static_cast<uint4*>(peers.out[p]) + out_row0_v;
+  const long long n = static_cast<long long>(batch) * dim_v;
+  for (long long i = static_cast<long long>(j) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(blocks_per_peer) * blockDim.x) {
+    const int b = static_cast<int>(i / dim_v);
+    const int c = static_cast<int>(i - static_cast<long long>(b) * dim_v);
+    dst[i] = x[b * batch_stride_v + c];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(peers.flags[p] + rank) : "memory");
+    if (j == 0) {
+      const unsigned int target = epoch * static_cast<unsigned int>(blocks_per_peer);
+      const unsigned int* mine = peers.flags[rank] + p;
+      const long long t0 = clock64();
+      unsigned int v;
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if (static_cast<int>(v - target) >= 0) break;
+        if (clock64() - t0 > 20000000000LL) {   // ~10 s: a peer died; surface it as a CUDA error, not a hang
+          printf("vt: pool_cls_allgather timeout rank %d waiting for rank %d (flag %u, want %u)\n", rank, p, v,
+                 target);
+          __trap();
+        }
+        __nanosleep(64);
+      }
+    }
+  }
+}
+
 }  // namespace
+
+int pool_cls_allgather(const void* x, int batch, int dim, long long batch_stride, int dtype,
+                       void* const* peer_out, unsigned int* const* peer_flags, int rank, int world,
+                       unsigned int epoch, cudaStream_t stream) {
+  if (!x || !peer_out || !peer_flags || batch <= 0 || dim <= 0 || world <= 0 || world > kMaxPeers ||
+      rank < 0 || rank >= world || epoch == 0)
+    return VT_ERR_ARG;
+  const int es = dtype == VT_F32 ? 4 : dtype == VT_BF16 ? 2 : 0;
+  if (es == 0) return VT_ERR_DTYPE;
+  const int per16 = 16 / es;
+  if ((dim % per16) || (batch_stride % per16) || (reinterpret_cast<uintptr_t>(x) & 15)) return VT_ERR_ALIGN;
+  PeerTable t;
+  for (int p = 0; p < world; ++p) {
+    if (!peer_out[p] || !peer_flags[p] || (reinterpret_cast<uintptr_t>(peer_out[p]) & 15)) return VT_ERR_ARG;
+    t.out[p] = peer_out[p];
+    t.flags[p] = peer_flags[p];
+  }
+  const int dim_v = dim / per16;
+  const long long n = static_cast<long long>(batch) * dim_v;
+  int blocks_per_peer = static_cast<int>((n + 512 * 8 - 1) / (512 * 8));   // ~8 vectors per thread
+  if (blocks_per_peer < 1) blocks_per_peer = 1;
+  if (blocks_per_peer > 8) blocks_per_peer = 8;
+  pool_cls_allgather_kernel<<<world * blocks_per_peer, 512, 0, stream>>>(
+      static_cast<const uint4*>(x), batch_stride / per16, batch, dim_v, t, rank, world, blocks_per_peer,
+      epoch, static_cast<long long>(rank) * batch * dim_v);
+  return static_cast<int>(cudaGetLastError());
+}
 
 int layernorm_rows(const void* x, const void* gamma, const void* beta, void* out, long long rows,
                    int dim, long long in_stride, long long out_stride, float eps, int in_dtype,

@@ -44,6 +44,8 @@ SIGNATURES = {
     "vt_conv2d": [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32,
                   _c_i32, _c_i32, _c_ptr],
     "vt_pool_cls": [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i64, _c_i32, _c_ptr],
+    "vt_pool_cls_allgather": [_c_ptr, _c_i32, _c_i32, _c_i64, _c_i32, _c_ptr, _c_ptr, _c_i32, _c_i32,
+                              ctypes.c_uint32, _c_ptr],
 }
 
 
