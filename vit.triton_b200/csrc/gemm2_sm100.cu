@@ -47,14 +47,14 @@ constexpr int kStagingBytes = 32 * kChunkCols * 2;      // 4 KB: 32 rows x 64 bf
 constexpr int kChunks = kColsPerWarp / kChunkCols;          // chunks per warp
 
 // Shared-memory split between operand stages and epilogue staging (227 KB in all):
-//   5 stages + one staging buffer per chunk (no reuse inside a tile)   -> epilogue-heavy launches
+//   5 stages + one staging buffer per chunk (no reuse inside a tile)   -> short-K residual launches
 //   6 stages + ONE staging buffer per epilogue warp (reused per chunk)  -> everything else
 // Five 32 KB stages cover ~3000 cycles of operand latency under load and the MMA issuer still waits
 // for operands 40 % of the time; the sixth stage shortens a QKV tile from 7313 to 6837 cycles and an
-// fc2 tile from 27073 to 26197, but serialising the two chunks of a warp on one staging buffer costs
-// the GELU epilogue (+3.8 %), the K = 768 residual epilogue (+4.2 %) and the LayerNorm-fold epilogue
-// (137 -> 151 us per launch) more than it gives.  In the C2 forward: plain QKV 117.7 -> 112.1 us,
-// fc2 + statistics 166.1 -> 162.8 us (CUPTI, same box).
+// fc2 tile from 27073 to 26197.  Serialising the two chunks of a warp on one staging buffer used to
+// cost the GELU and LayerNorm-fold epilogues more than that; with the paced epilogue (the chunks are
+// spread over the tile anyway) only the K = 768 residual epilogue still prefers two buffers
+// (66.2k vs 70.9k cycles per out-proj launch).
 template <int kStagesT, int kStageBufsT>
 struct G2Cfg {
   static constexpr int kStages = kStagesT;
@@ -438,7 +438,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       if (ahead) mbar_wait(tfull_bar(as), aphase);
       if (p.dbg) { const long long w1 = clock64(); dbg_acc[0] += w1 - w0; w0 = w1; }
       tc_fence_after();
-      const bool paced = ahead && p.pace > 0;
+      // (the CTA's last tile has no mainloop left to protect: pacing it would only lengthen the tail)
+      const bool paced = ahead && p.pace > 0 && (t + tile_step < num_tiles);
       const long long pace_t0 = paced ? clock64() + q * p.pace_q : 0;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + cgrp * kColsPerWarp;
 
@@ -682,10 +683,12 @@ int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long l
   if (ideal > 6144) ideal = 6144;
   p.pace = static_cast<int>(ideal * pace_pm / 1000);
   p.pace_q = static_cast<int>(ideal * pace_q_pm / 1000);
-  // Shared-memory split per epilogue (see G2Cfg): GELU and short-K residual epilogues keep two staging
-  // buffers per warp, everything else (the LayerNorm fold included, now that its operands are
-  // prefetched: 7947 -> 7050 cycles per tile) takes the sixth operand stage.  VT_GEMM_STAGES=5|6 forces
-  // one for every launch, VT_LNF_STAGES=5|6 for the LayerNorm-fold launches only.
+  // Shared-memory split per epilogue (see G2Cfg): only the short-K residual epilogue (out-proj: its
+  // residual chunks are TMA-prefetched into the staging buffers) keeps two staging buffers per warp;
+  // everything else takes the sixth operand stage — with the paced epilogue and the prefetched
+  // operands that now also holds for GELU (215.7k -> 209.4k cycles per fc1 launch) and the LayerNorm
+  // fold (7947 -> 7050 cycles per tile).  VT_GEMM_STAGES=5|6 forces one for every launch,
+  // VT_LNF_STAGES=5|6 for the LayerNorm-fold launches only.
   static const int forced = [] {
     const char* e = getenv("VT_GEMM_STAGES");
     return (e && (e[0] == '5' || e[0] == '6')) ? (e[0] - '0') : 0;
@@ -694,7 +697,7 @@ int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long l
     const char* e = getenv("VT_LNF_STAGES");
     return (e && (e[0] == '5' || e[0] == '6')) ? (e[0] - '0') : 0;
   }();
-  const bool epilogue_heavy = gelu || (residual && K < 2048);
+  const bool epilogue_heavy = residual && K < 2048;
   bool deep = forced ? (forced == 6) : !epilogue_heavy;
   if (rowstats && forced_lnf) deep = (forced_lnf == 6);
 #define VT_G2_LAUNCH(E) (deep ? launch2<E, G2Deep>(ta, tb, to, tr, p, stream) : launch2<E, G2Wide>(ta, tb, to, tr, p, stream))
