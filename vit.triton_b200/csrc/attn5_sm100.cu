@@ -58,7 +58,12 @@ struct Attn5Params {
 };
 
 enum { C_QFULL = 0, C_QEMPTY = 2, C_KFULL = 4, C_KEMPTY = 6, C_VFULL = 8, C_VEMPTY = 10, C_SFULL = 12,
-       C_PFULL = 14, C_OFULL = 16, C_OREAD = 18, C_NBARS = 19 };
+       C_PFULL = 14, C_OFULL = 16, C_OREAD = 18, C_PHALF = 19, C_NBARS = 21 };
+// C_PHALF (experiment, -DVT_ATTN5_SPLIT): the first (up to) four 16-column groups of every softmax
+// warp's P are in TMEM — the MMA issuer starts O = P V on those keys while the second part of the exp
+// pass is still running.  Measured SLOWER (79.6 vs 75.0 us per launch at C2): the mid-pass
+// tcgen05.wait::st + fence + arrive costs the exp pass more than the shorter wait for O gives back.
+[[maybe_unused]] constexpr int kSplitGroups5 = 4;
 
 __device__ __noinline__ void mbar_wait_slow5(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void mbar_wait_lean5(uint32_t bar, uint32_t parity) {
@@ -129,7 +134,8 @@ __device__ __forceinline__ void exp_group5(const uint32_t (&r)[16], uint32_t dst
 // a + 8g .. a + 8g + 7 (scores this thread has already consumed).  Groups are loaded in pairs, the
 // next pair is in flight during the math of the current one.
 template <int NG>
-__device__ __forceinline__ void exp_groups5(uint32_t a, int nv, float scale_log2, float m) {
+__device__ __forceinline__ void exp_groups5(uint32_t a, int nv, float scale_log2, float m, uint32_t half_bar,
+                                            int lane) {
   constexpr int kPairs = (NG + 1) / 2;
   uint32_t r[kPairs][2][16];
   auto load_pair = [&](int pr) {
@@ -151,6 +157,14 @@ __device__ __forceinline__ void exp_groups5(uint32_t a, int nv, float scale_log2
           exp_group5<true>(r[pr][h], a + 8 * g, nv - 16 * (NG - 1), scale_log2, m);
       }
     }
+#ifdef VT_ATTN5_SPLIT
+    if (pr == (kPairs >= 2 ? 1 : 0)) {   // min(NG, kSplitGroups5) groups of P are written: hand them over
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(half_bar);
+    }
+#endif
   }
   tmem_st_wait();
 }
@@ -186,7 +200,7 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
 
   if (warp_idx == 17 && lane == 0) {
     for (int i = 0; i < C_NBARS; ++i)
-      mbar_init(bar(i), (i == C_PFULL || i == C_PFULL + 1 || i == C_OREAD) ? 8 : 1);
+      mbar_init(bar(i), (i == C_PFULL || i == C_PFULL + 1 || i == C_OREAD || i == C_PHALF || i == C_PHALF + 1) ? 8 : 1);
     fence_barrier_init();
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_k);
@@ -289,25 +303,50 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       VT_MTICK(0)
       if (v > 0) mbar_wait(bar(C_OREAD), static_cast<uint32_t>(v - 1) & 1u);   // O columns free
       VT_MTICK(1)
+      const uint32_t idesc = make_idesc_bf16(kQTile5, kDH5, 0, 1);
+      const uint32_t idesc_l = make_idesc_bf16(kQTile5, 16, 0, 1);
+      const uint64_t vd = make_desc_mnmajor_sw128(v_smem + b * kv_bytes, 1024);
+      const uint64_t od = make_smem_desc(ones_smem, 256, 256, 6);   // every element is 1: layout is moot
+      const uint32_t s_tmem = tmem_base + b * kSCols5;
+      // 16 keys: 8 packed P columns, 2048 B of V.  P of group k lives at the start of its owner's
+      // columns: half 0 owns groups [0, ng0)
+      auto pv_step = [&](int k, uint32_t acc) {
+        const uint32_t a_tmem = s_tmem + (k < ng0 ? 8 * k : 16 * ng0 + 8 * (k - ng0));
+        umma_ts(tmem_base + kOCol5, a_tmem, vd + 128 * k, idesc, acc);
+        umma_ts(tmem_base + kLCol5, a_tmem, od, idesc_l, acc);
+      };
+#ifdef VT_ATTN5_SPLIT
+      // first part: the (up to) four leading groups of each column half, ready half-way through the exp pass
+      const int na0 = ng0 < kSplitGroups5 ? ng0 : kSplitGroups5;
+      const int na1 = (n16 - ng0) < kSplitGroups5 ? (n16 - ng0) : kSplitGroups5;
+      mbar_wait(bar(C_PHALF + b), ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        for (int k = 0; k < na0; ++k) pv_step(k, k != 0 ? 1u : 0u);
+        for (int k = ng0; k < ng0 + na1; ++k) pv_step(k, 1u);
+      }
+      __syncwarp();
       mbar_wait(bar(C_PFULL + b), ph);
       VT_MTICK(2)
       tc_fence_after();
       if (elect_one_sync()) {
-        const uint32_t idesc = make_idesc_bf16(kQTile5, kDH5, 0, 1);
-        const uint32_t idesc_l = make_idesc_bf16(kQTile5, 16, 0, 1);
-        const uint64_t vd = make_desc_mnmajor_sw128(v_smem + b * kv_bytes, 1024);
-        const uint64_t od = make_smem_desc(ones_smem, 256, 256, 6);   // every element is 1: layout is moot
-        const uint32_t s_tmem = tmem_base + b * kSCols5;
-        for (int k = 0; k < n16; ++k) {   // 16 keys: 8 packed P columns, 2048 B of V
-          // P of group k lives at the start of its owner's columns: half 0 owns groups [0, ng0)
-          const uint32_t a_tmem = s_tmem + (k < ng0 ? 8 * k : 16 * ng0 + 8 * (k - ng0));
-          umma_ts(tmem_base + kOCol5, a_tmem, vd + 128 * k, idesc, k != 0 ? 1u : 0u);
-          umma_ts(tmem_base + kLCol5, a_tmem, od, idesc_l, k != 0 ? 1u : 0u);
-        }
+        for (int k = na0; k < ng0; ++k) pv_step(k, 1u);
+        for (int k = ng0 + na1; k < n16; ++k) pv_step(k, 1u);
         umma_commit(bar(C_OFULL + b));
         umma_commit(bar(C_VEMPTY + b));
       }
       __syncwarp();
+#else
+      mbar_wait(bar(C_PFULL + b), ph);
+      VT_MTICK(2)
+      tc_fence_after();
+      if (elect_one_sync()) {
+        for (int k = 0; k < n16; ++k) pv_step(k, k != 0 ? 1u : 0u);
+        umma_commit(bar(C_OFULL + b));
+        umma_commit(bar(C_VEMPTY + b));
+      }
+      __syncwarp();
+#endif
       if (v + 2 < n_items) issue_scores(v + 2);
       VT_MTICK(3)
     }
@@ -379,18 +418,21 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         VT_TICK5(2)
         // pass 2: exponentials; P overwrites my own consumed scores
         switch (ng) {
-          case 7: exp_groups5<7>(t_mine, nvr, p.scale_log2, m); break;
-          case 6: exp_groups5<6>(t_mine, nvr, p.scale_log2, m); break;
-          case 5: exp_groups5<5>(t_mine, nvr, p.scale_log2, m); break;
-          case 4: exp_groups5<4>(t_mine, nvr, p.scale_log2, m); break;
-          case 3: exp_groups5<3>(t_mine, nvr, p.scale_log2, m); break;
-          case 2: exp_groups5<2>(t_mine, nvr, p.scale_log2, m); break;
-          case 1: exp_groups5<1>(t_mine, nvr, p.scale_log2, m); break;
+          case 7: exp_groups5<7>(t_mine, nvr, p.scale_log2, m, bar(C_PHALF + g), lane); break;
+          case 6: exp_groups5<6>(t_mine, nvr, p.scale_log2, m, bar(C_PHALF + g), lane); break;
+          case 5: exp_groups5<5>(t_mine, nvr, p.scale_log2, m, bar(C_PHALF + g), lane); break;
+          case 4: exp_groups5<4>(t_mine, nvr, p.scale_log2, m, bar(C_PHALF + g), lane); break;
+          case 3: exp_groups5<3>(t_mine, nvr, p.scale_log2, m, bar(C_PHALF + g), lane); break;
+          case 2: exp_groups5<2>(t_mine, nvr, p.scale_log2, m, bar(C_PHALF + g), lane); break;
+          case 1: exp_groups5<1>(t_mine, nvr, p.scale_log2, m, bar(C_PHALF + g), lane); break;
           default: break;
         }
       }
       tc_fence_before();
       __syncwarp();
+#ifdef VT_ATTN5_SPLIT
+      if (lane == 0 && (!live || ng == 0)) mbar_arrive(bar(C_PHALF + g));   // warps that skipped the exp pass
+#endif
       if (lane == 0) mbar_arrive(bar(C_PFULL + g));
       VT_TICK5(3)
 
@@ -580,7 +622,7 @@ attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
 
   if (warp_idx == 17 && lane == 0) {
     for (int i = 0; i < C_NBARS; ++i)
-      mbar_init(bar(i), (i == C_PFULL || i == C_PFULL + 1 || i == C_OREAD) ? 8 : 1);
+      mbar_init(bar(i), (i == C_PFULL || i == C_PFULL + 1 || i == C_OREAD || i == C_PHALF || i == C_PHALF + 1) ? 8 : 1);
     fence_barrier_init();
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_k);
