@@ -111,6 +111,13 @@ int vt_patch_embed(const void* pixels, int32_t pix_dtype, const void* w, int64_t
                    const float* posb, void* out, int32_t out_dtype, int32_t B, int32_t C, int32_t S,
                    int32_t P, int32_t D, void* stream);
 
+/* The same, also writing the (sum, sumsq) of every 128-column group of every output row (CLS rows
+ * included) to stats_out[(row*(D/128) + group)*2 .. +1] — the rowstats layout of vt_gemm_bf16_ln, so the
+ * first block's layernorm_before folds into its QKV GEMM too.  D % 128 == 0. */
+int vt_patch_embed_stats(const void* pixels, int32_t pix_dtype, const void* w, int64_t ldw,
+                         const float* posb, void* out, int32_t out_dtype, float* stats_out, int32_t B,
+                         int32_t C, int32_t S, int32_t P, int32_t D, void* stream);
+
 /* (B,C,H,W) -> (B, (H/P)*(W/P), C*P*P) patch rows in (c,i,j) order.
  * Replaces patching_triton (vit/kernels/patching.py:54-92). */
 int vt_patching(const void* image, void* out, int32_t B, int32_t C, int32_t H, int32_t W, int32_t P,

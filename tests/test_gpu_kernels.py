@@ -334,6 +334,14 @@ def test_patch_embed_fused(S, P, D, B, pix_dtype):
     assert got.shape == (B, n + 1, D) and got.dtype == torch.bfloat16
     assert rel_err(got, want) <= 2 ** -7, f"rel err {rel_err(got, want)}"
     assert (got.float() - want).abs().max().item() <= 0.05
+    if D % 128 == 0:
+        # the same launch with the row statistics for the LayerNorm folded into block 0's QKV GEMM
+        stats = torch.full((B * (n + 1), D // 128, 2), float("nan"), device=dev())
+        again = emb(x, stats)
+        assert torch.equal(again, got)
+        wc = want.reshape(B * (n + 1), D // 128, 128)
+        assert torch.allclose(stats[..., 0], wc.sum(-1), rtol=1e-3, atol=2e-2)
+        assert torch.allclose(stats[..., 1], (wc * wc).sum(-1), rtol=1e-3, atol=2e-2)
 
 
 @pytest.mark.parametrize("S,P,D,B", [(224, 16, 768, 3), (64, 16, 128, 5), (56, 14, 160, 2), (224, 14, 1280, 1), (96, 32, 64, 2)])

@@ -38,7 +38,7 @@ int attn5_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, in
                       long long, long long, long long, float, int, cudaStream_t);
 int attn5mb_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
                         long long, long long, long long, float, int, cudaStream_t);
-int patch_embed_tcgen05(const void*, int, const void*, long long, const float*, void*, int, int,
+int patch_embed_tcgen05(const void*, int, const void*, long long, const float*, void*, int, float*, int,
                         int, int, int, int, cudaStream_t);
 int patching(const void*, void*, int, int, int, int, int, int, cudaStream_t);
 int embed_finalize(void*, const void*, const void*, int, int, int, int, cudaStream_t);
@@ -179,7 +179,14 @@ int vt_flash_attn(const void* q, const void* k, const void* v, void* out, int32_
 int vt_patch_embed(const void* pixels, int32_t pix_dtype, const void* w, int64_t ldw,
                    const float* posb, void* out, int32_t out_dtype, int32_t B, int32_t C, int32_t S_,
                    int32_t P, int32_t D, void* stream) {
-  return vt::patch_embed_tcgen05(pixels, pix_dtype, w, ldw, posb, out, out_dtype, B, C, S_, P, D,
+  return vt::patch_embed_tcgen05(pixels, pix_dtype, w, ldw, posb, out, out_dtype, nullptr, B, C, S_, P, D,
+                                 S(stream));
+}
+
+int vt_patch_embed_stats(const void* pixels, int32_t pix_dtype, const void* w, int64_t ldw,
+                         const float* posb, void* out, int32_t out_dtype, float* stats_out, int32_t B,
+                         int32_t C, int32_t S_, int32_t P, int32_t D, void* stream) {
+  return vt::patch_embed_tcgen05(pixels, pix_dtype, w, ldw, posb, out, out_dtype, stats_out, B, C, S_, P, D,
                                  S(stream));
 }
 

@@ -688,7 +688,7 @@ int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long l
   // everything else takes the sixth operand stage — with the paced epilogue and the prefetched
   // operands that now also holds for GELU (215.7k -> 209.4k cycles per fc1 launch) and the LayerNorm
   // fold (7947 -> 7050 cycles per tile).  VT_GEMM_STAGES=5|6 forces one for every launch,
-  // VT_LNF_STAGES=5|6 for the LayerNorm-fold launches only.
+  // VT_LNF_STAGES=5|6 for the LayerNorm-fold launches only, VT_GELU_STAGES=5|6 for the GELU launches.
   static const int forced = [] {
     const char* e = getenv("VT_GEMM_STAGES");
     return (e && (e[0] == '5' || e[0] == '6')) ? (e[0] - '0') : 0;
@@ -700,6 +700,11 @@ int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long l
   const bool epilogue_heavy = residual && K < 2048;
   bool deep = forced ? (forced == 6) : !epilogue_heavy;
   if (rowstats && forced_lnf) deep = (forced_lnf == 6);
+  static const int forced_gelu = [] {
+    const char* e = getenv("VT_GELU_STAGES");
+    return (e && (e[0] == '5' || e[0] == '6')) ? (e[0] - '0') : 0;
+  }();
+  if (gelu && forced_gelu) deep = (forced_gelu == 6);
 #define VT_G2_LAUNCH(E) (deep ? launch2<E, G2Deep>(ta, tb, to, tr, p, stream) : launch2<E, G2Wide>(ta, tb, to, tr, p, stream))
   if (rowstats && !colsum) return gelu ? VT_G2_LAUNCH(EPI_LNF | EPI_NOCS | EPI_GELU) : VT_G2_LAUNCH(EPI_LNF | EPI_NOCS);
   if (rowstats) return gelu ? VT_G2_LAUNCH(EPI_LNF | EPI_GELU) : VT_G2_LAUNCH(EPI_LNF);

@@ -53,6 +53,9 @@ struct PatchParams {
   const float* posb;    // [n_patches + 1, D] fp32: pos + (cls | conv bias)
   void* out;            // [B, n_patches + 1, D]
   int out_f32;
+  // optional: (sum, sumsq) of every 128-column group of every output row, [(B * (n_patches + 1)), D / 128, 2]
+  // — the row statistics the LayerNorm folded into the first QKV GEMM consumes (gemm2_sm100.cu)
+  float* stats;
 };
 
 __device__ __forceinline__ float px_to_f(float v) { return v; }
@@ -302,6 +305,7 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const Patc
       }
     };
     float4 pb_cur[4], pb_nxt[4];
+    float2 st_sum2 = make_float2(0.f, 0.f), st_sq2 = make_float2(0.f, 0.f);   // this warp's 128 columns of the row
     load_posb(pb_cur, col_base);
     mbar_wait(acc_bar, 0);
     tc_fence_after();
@@ -323,6 +327,9 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const Patc
                                        make_float2(pb_cur[i].z, pb_cur[i].w));
           v[4 * i + 0] = lo.x; v[4 * i + 1] = lo.y;
           v[4 * i + 2] = hi.x; v[4 * i + 3] = hi.y;
+          st_sum2 = __fadd2_rn(st_sum2, __fadd2_rn(lo, hi));
+          st_sq2 = __ffma2_rn(lo, lo, st_sq2);
+          st_sq2 = __ffma2_rn(hi, hi, st_sq2);
         }
         const bool full_chunk = col + kStep <= p.D;
         if (p.out_f32) {
@@ -355,7 +362,30 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const Patc
       for (int i = 0; i < 4; ++i) pb_cur[i] = pb_nxt[i];
     }
 
+    if (p.stats != nullptr && e_valid && col_base < p.D) {   // D % 128 == 0 (host): the group is all in or all out
+      float2* dst = reinterpret_cast<float2*>(p.stats) + out_row * (p.D >> 7) + (col_base >> 7);
+      *dst = make_float2(st_sum2.x + st_sum2.y, st_sq2.x + st_sq2.y);
+    }
+
     // CLS rows: the first row-tile of every column block writes cls + pos[0] for all images.
+    if (m_blk == 0 && p.stats != nullptr) {
+      // their statistics: the same two 128-column groups for every image (one thread per (image, group))
+      const int groups = min(PE_BN, p.D - n_blk * PE_BN) >> 7;
+      for (int idx = threadIdx.x; idx < p.B * groups; idx += PE_GATHER_THREADS) {
+        const int b = idx / groups;
+        const int gidx = idx - b * groups;
+        const float* src = p.posb + n_blk * PE_BN + gidx * 128;
+        float sx = 0.f, sq = 0.f;
+        for (int c = 0; c < 128; ++c) {
+          const float val = __ldg(src + c);
+          sx += val;
+          sq = fmaf(val, val, sq);
+        }
+        float2* dst = reinterpret_cast<float2*>(p.stats) + static_cast<long long>(b) * n_tok * (p.D >> 7) +
+                      ((n_blk * PE_BN) >> 7) + gidx;
+        *dst = make_float2(sx, sq);
+      }
+    }
     if (m_blk == 0) {
       const int ncols = min(PE_BN, p.D - n_blk * PE_BN);
       const int total = p.B * ncols;
@@ -395,12 +425,14 @@ int launch_patch(const CUtensorMap& tw, const PatchParams& p, dim3 grid, cudaStr
 // the matching k order with row stride ldw (elements, multiple of 8), posb [n+1, D] fp32,
 // out [B, n+1, D] bf16|f32.
 int patch_embed_tcgen05(const void* pixels, int pix_dtype, const void* w, long long ldw,
-                        const float* posb, void* out, int out_dtype, int B, int C, int S, int P,
+                        const float* posb, void* out, int out_dtype, float* stats, int B, int C, int S, int P,
                         int D, cudaStream_t stream) {
   if (!pixels || !w || !posb || !out || B <= 0 || C <= 0 || S <= 0 || P <= 0 || D <= 0)
     return VT_ERR_ARG;
   if (S % P) return VT_ERR_ARG;
   if ((ldw % 8) || (D % 8)) return VT_ERR_ALIGN;
+  if (stats && (D % 128)) return VT_ERR_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(stats) & 7) return VT_ERR_ALIGN;
   if ((reinterpret_cast<uintptr_t>(pixels) | reinterpret_cast<uintptr_t>(w) |
        reinterpret_cast<uintptr_t>(posb) | reinterpret_cast<uintptr_t>(out)) & 15)
     return VT_ERR_ALIGN;
@@ -419,6 +451,7 @@ int patch_embed_tcgen05(const void* pixels, int pix_dtype, const void* w, long l
   p.posb = posb;
   p.out = out;
   p.out_f32 = (out_dtype == VT_F32);
+  p.stats = stats;
   if (out_dtype != VT_F32 && out_dtype != VT_BF16) return VT_ERR_DTYPE;
 
   const long long M = static_cast<long long>(B) * p.n_patches;

@@ -184,7 +184,8 @@ def pack_embeddings_u8(emb, image_mean, image_std, rescale_factor: float) -> Sim
     return SimpleNamespace(w=w2d, ldw=kpad, K=K, posb=posb.contiguous())
 
 
-def patch_embed_u8(emb, x: torch.Tensor, image_mean, image_std, rescale_factor: float) -> torch.Tensor:
+def patch_embed_u8(emb, x: torch.Tensor, image_mean, image_std, rescale_factor: float,
+                   stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Raw uint8 NHWC pixels (B, S, S, C) -> token embeddings (B, n+1, D), rescale + normalise + patch
     projection + CLS + position embeddings in ONE kernel (bf16 models on the tensor-core path)."""
     w = emb.projection.weight
@@ -214,8 +215,9 @@ def patch_embed_u8(emb, x: torch.Tensor, image_mean, image_std, rescale_factor: 
     step = 65535 * 128 // emb.num_patches
     for b0 in range(0, B, step):
         nb = min(step, B - b0)
-        _lib.call("vt_patch_embed", x[b0:].data_ptr(), _lib.VT_U8, pk.w.data_ptr(), pk.ldw, pk.posb.data_ptr(),
-                  out[b0:].data_ptr(), _lib.VT_BF16, nb, C, S, emb.patch_size, emb.hidden_dim, stream)
+        _embed_call(stats, b0, n_tok, emb.hidden_dim, x[b0:].data_ptr(), _lib.VT_U8, pk.w.data_ptr(), pk.ldw,
+                    pk.posb.data_ptr(), out[b0:].data_ptr(), _lib.VT_BF16, nb, C, S, emb.patch_size,
+                    emb.hidden_dim, stream)
     return out
 
 
@@ -289,8 +291,19 @@ def linear(x: torch.Tensor, w_nk: torch.Tensor, bias32: torch.Tensor, gelu: bool
     return out
 
 
-def patch_embed(emb, x: torch.Tensor) -> torch.Tensor:
-    """Pixels (B, C, S, S) -> token embeddings (B, n+1, D) including CLS and position embeddings."""
+def _embed_call(stats, b0, n_tok, dim, *args):
+    """vt_patch_embed, or vt_patch_embed_stats writing the row statistics of images b0.. into ``stats``."""
+    if stats is None:
+        _lib.call("vt_patch_embed", *args)
+        return
+    s_ptr = stats.data_ptr() + b0 * n_tok * (dim // STATS_COLS) * 2 * 4
+    _lib.call("vt_patch_embed_stats", *args[:7], s_ptr, *args[7:])
+
+
+def patch_embed(emb, x: torch.Tensor, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Pixels (B, C, S, S) -> token embeddings (B, n+1, D) including CLS and position embeddings.
+    ``stats``: optional (B * (n+1), D/128, 2) fp32 buffer for the row statistics the LayerNorm folded
+    into the first QKV GEMM consumes (bf16 tensor-core path only)."""
     pk = emb.packed()
     w = emb.projection.weight
     B, C, S, _ = x.shape
@@ -307,9 +320,10 @@ def patch_embed(emb, x: torch.Tensor) -> torch.Tensor:
         step = 65535 * 128 // emb.num_patches
         for b0 in range(0, B, step):
             nb = min(step, B - b0)
-            _lib.call("vt_patch_embed", x[b0:].data_ptr(), _lib.dtype_code(x), pk.w.data_ptr(), pk.ldw,
-                      pk.posb.data_ptr(), out[b0:].data_ptr(), _lib.VT_BF16, nb, C, S, P, D, stream)
+            _embed_call(stats, b0, n_tok, D, x[b0:].data_ptr(), _lib.dtype_code(x), pk.w.data_ptr(), pk.ldw,
+                        pk.posb.data_ptr(), out[b0:].data_ptr(), _lib.VT_BF16, nb, C, S, P, D, stream)
         return out
+    assert stats is None, "Row statistics come out of the bf16 tensor-core patch embedding only"
 
     # exact path: im2col rows, strided GEMM straight into rows 1..n of every image, then CLS/pos
     from .kernels.patching import patching

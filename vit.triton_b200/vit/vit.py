@@ -216,12 +216,16 @@ class Encoder(nn.Module):
             for _ in range(self.num_layers)
         )
 
-    def forward(self, x) -> torch.Tensor:
-        if _FUSED and _FOLD_LN and len(self.layer) > 0 and x.numel() > 0 and \
-                packing.folding_supported(x, self.hidden_dim, self.layer[0].mlp_dim):
-            # layernorm_before of blocks 1.. folded into their QKV GEMM; row statistics of each block's
-            # output are produced by its last GEMM's epilogue
-            ln1_stats = None
+    def folding_active(self, x) -> bool:
+        return bool(_FUSED and _FOLD_LN and len(self.layer) > 0 and x.numel() > 0 and
+                    packing.folding_supported(x, self.hidden_dim, self.layer[0].mlp_dim))
+
+    def forward(self, x, ln1_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``ln1_stats``: row statistics of x written by the patch-embedding epilogue (see
+        ``Embeddings.forward``); without them block 0's layernorm_before runs as a kernel."""
+        if self.folding_active(x):
+            # layernorm_before folded into the QKV GEMM; row statistics of each block's output are
+            # produced by its last GEMM's epilogue
             for layer in self.layer:
                 x, ln1_stats = layer.forward_folded(x, ln1_stats)
             return x
@@ -249,8 +253,11 @@ class Embeddings(packing.PackedMixin, nn.Module):
             kernel_size=(self.patch_size, self.patch_size)
         )
 
-    def forward(self, x) -> torch.Tensor:
+    def forward(self, x, stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``stats_out`` (optional, fused bf16 path only): (B * N, D/128, 2) fp32 buffer that receives the
+        row statistics of the output for the LayerNorm folded into block 0's QKV GEMM."""
         if not (_FUSED and x.is_cuda):
+            assert stats_out is None
             tokens = self.projection(x.to(self.projection.weight.dtype)).flatten(2).transpose(1, 2)
             out = torch.empty((x.shape[0], self.num_patches + 1, self.hidden_dim), device=x.device,
                               dtype=tokens.dtype)
@@ -259,14 +266,14 @@ class Embeddings(packing.PackedMixin, nn.Module):
                       self.cls_token.data_ptr(), out.shape[0], out.shape[1], out.shape[2],
                       _lib.dtype_code(out), _lib.stream_ptr(out))
             return out
-        return packing.patch_embed(self, x)
+        return packing.patch_embed(self, x, stats_out)
 
     def forward_uint8(self, x, image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5),
-                      rescale_factor: float = 1.0 / 255.0) -> torch.Tensor:
+                      rescale_factor: float = 1.0 / 255.0, stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Raw uint8 NHWC pixels (B, H, W, C) -> embeddings: the image processor's rescale and
         normalisation (defaults: HF ``ViTImageProcessor`` of google/vit-base-patch16-224) are folded
         into the patch projection, see ``packing.pack_embeddings_u8``."""
-        return packing.patch_embed_u8(self, x, image_mean, image_std, rescale_factor)
+        return packing.patch_embed_u8(self, x, image_mean, image_std, rescale_factor, stats_out)
 
     def _packed_sources(self):
         return [self.cls_token, self.position_embeddings, self.projection.weight, self.projection.bias]
@@ -344,10 +351,23 @@ class VIT(nn.Module):
 
     def forward(self, x):
         assert x.shape[1:] == (self.channels, self.height, self.width), f"Image size {x.shape[1:]} not matching with the model input size: {self.channels, self.height, self.width}"
-        x = self.embeddings(x)
-        x = self.encoder(x)
+        stats = self._embed_stats(x.shape[0], x.device)
+        x = self.embeddings(x, stats) if stats is not None else self.embeddings(x)
+        x = self.encoder(x, stats) if stats is not None else self.encoder(x)
         x = self.layernorm(x)
         return x
+
+    def _embed_stats(self, batch: int, device) -> Optional[torch.Tensor]:
+        """Buffer for the row statistics of the embeddings when block 0's layernorm_before is folded
+        into its QKV GEMM (fused bf16 CUDA path, hidden size a multiple of 128); None otherwise."""
+        w = self.embeddings.projection.weight
+        if not (w.is_cuda and w.dtype == torch.bfloat16 and batch > 0 and self.hidden_dim % 8 == 0):
+            return None
+        probe = torch.empty((1,), device=device, dtype=w.dtype)
+        if not self.encoder.folding_active(probe):
+            return None
+        n_tok = self.embeddings.num_patches + 1
+        return torch.empty((batch * n_tok, self.hidden_dim // packing.STATS_COLS, 2), device=device, dtype=torch.float32)
 
     def forward_uint8(self, x, image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5),
                       rescale_factor: float = 1.0 / 255.0):
@@ -355,8 +375,9 @@ class VIT(nn.Module):
         ``forward``: rescale + normalise (HF ``ViTImageProcessor``) run inside the patch-embedding
         kernel, so the host -> device copy is one byte per pixel value."""
         assert tuple(x.shape[1:]) == (self.height, self.width, self.channels), f"Image size {x.shape[1:]} not matching with the model input size: {self.height, self.width, self.channels}"
-        x = self.embeddings.forward_uint8(x, image_mean, image_std, rescale_factor)
-        x = self.encoder(x)
+        stats = self._embed_stats(x.shape[0], x.device)
+        x = self.embeddings.forward_uint8(x, image_mean, image_std, rescale_factor, stats)
+        x = self.encoder(x, stats) if stats is not None else self.encoder(x)
         x = self.layernorm(x)
         return x
 
