@@ -13,12 +13,15 @@
 // issues MMAs (M=256, N=256, K=16); both CTAs' TMA loads complete on the leader's mbarrier.
 //
 // Epilogue: 8 warps per CTA; warp (q, g) owns TMEM lanes 32q..32q+31 and columns 128g..128g+127
-// (16 warps x 64 columns measured no faster: the GELU epilogue is not latency-bound).
-// Per 64-column chunk: tcgen05.ld -> +bias -> (+residual from smem) -> (GELU) -> bf16 ->
-// SWIZZLE_128B staging buffer -> TMA store.  The residual chunk is TMA-LOADED into the same staging
-// buffer before the accumulator is ready, so neither residual reads nor output writes go through
-// per-thread global accesses (the v1 row-per-thread stores made the epilogue the bottleneck:
-// profiles/r01_*).
+// (16 warps x 64 columns measured no faster).  Per 64-column chunk: tcgen05.ld -> +bias (lane-owned,
+// broadcast with shuffles) -> (LayerNorm fold: x rstd of the row) -> (+residual from smem) -> (GELU) ->
+// bf16 -> SWIZZLE_128B staging buffer -> TMA store.  The residual chunk is TMA-LOADED into the same
+// staging buffer before the accumulator is ready, so neither residual reads nor output writes go
+// through per-thread global accesses (the v1 row-per-thread stores made the epilogue the bottleneck:
+// profiles/r01_*).  The chunks of the eight warps are PACED over the tile (see the epilogue) because
+// simultaneous store bursts collide with the operand stream on the SM's L2 port; per-tile operands
+// (bias, row statistics of the folded LayerNorm) are prefetched one tile ahead because with 224 KB of
+// shared memory configured there is no L1 and every global load is an L2 round trip.
 #include <cstdlib>
 
 #include "common.cuh"
