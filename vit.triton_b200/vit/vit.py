@@ -351,23 +351,26 @@ class VIT(nn.Module):
 
     def forward(self, x):
         assert x.shape[1:] == (self.channels, self.height, self.width), f"Image size {x.shape[1:]} not matching with the model input size: {self.channels, self.height, self.width}"
-        stats = self._embed_stats(x.shape[0], x.device)
+        stats = self._embed_stats(x)
         x = self.embeddings(x, stats) if stats is not None else self.embeddings(x)
         x = self.encoder(x, stats) if stats is not None else self.encoder(x)
         x = self.layernorm(x)
         return x
 
-    def _embed_stats(self, batch: int, device) -> Optional[torch.Tensor]:
+    def _embed_stats(self, x: torch.Tensor) -> Optional[torch.Tensor]:
         """Buffer for the row statistics of the embeddings when block 0's layernorm_before is folded
-        into its QKV GEMM (fused bf16 CUDA path, hidden size a multiple of 128); None otherwise."""
+        into its QKV GEMM (fused bf16 tensor-core path, hidden size a multiple of 128); None otherwise."""
         w = self.embeddings.projection.weight
-        if not (w.is_cuda and w.dtype == torch.bfloat16 and batch > 0 and self.hidden_dim % 8 == 0):
+        batch = x.shape[0]
+        if not (x.is_cuda and w.is_cuda and w.dtype == torch.bfloat16 and batch > 0 and self.hidden_dim % 8 == 0
+                and x.dtype in (torch.float32, torch.bfloat16, torch.uint8)):
             return None
-        probe = torch.empty((1,), device=device, dtype=w.dtype)
+        probe = torch.empty((1,), device=x.device, dtype=w.dtype)
         if not self.encoder.folding_active(probe):
             return None
         n_tok = self.embeddings.num_patches + 1
-        return torch.empty((batch * n_tok, self.hidden_dim // packing.STATS_COLS, 2), device=device, dtype=torch.float32)
+        return torch.empty((batch * n_tok, self.hidden_dim // packing.STATS_COLS, 2), device=x.device,
+                           dtype=torch.float32)
 
     def forward_uint8(self, x, image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5),
                       rescale_factor: float = 1.0 / 255.0):
@@ -375,7 +378,7 @@ class VIT(nn.Module):
         ``forward``: rescale + normalise (HF ``ViTImageProcessor``) run inside the patch-embedding
         kernel, so the host -> device copy is one byte per pixel value."""
         assert tuple(x.shape[1:]) == (self.height, self.width, self.channels), f"Image size {x.shape[1:]} not matching with the model input size: {self.height, self.width, self.channels}"
-        stats = self._embed_stats(x.shape[0], x.device)
+        stats = self._embed_stats(x)
         x = self.embeddings.forward_uint8(x, image_mean, image_std, rescale_factor, stats)
         x = self.encoder(x, stats) if stats is not None else self.encoder(x)
         x = self.layernorm(x)
