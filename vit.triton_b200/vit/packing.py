@@ -114,7 +114,9 @@ def _fold_layernorm_zero_sum(w_nk: torch.Tensor, bias32: torch.Tensor, ln, passe
         for _ in range(passes):
             f = wz.float()
             resid = f.double().sum(dim=1).float()[:, None]                   # (N, 1): what has to go
-            ulp = torch.exp2(torch.floor(torch.log2(f.abs().clamp_min(1e-30))) - 7.0)
+            # one bf16 ulp of every element: 2^(exponent - 7), built from the exponent field (integer ops only)
+            expo = (f.view(torch.int32) >> 23) & 0xFF
+            ulp = ((expo - 7).clamp_min(1) << 23).view(torch.float32)
             err = exact - f                                                  # rounding error so far
             ok = ~moved & (ulp <= resid.abs())
             # added squared error per unit of residue removed: small for elements that were rounded
