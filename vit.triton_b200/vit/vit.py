@@ -38,10 +38,12 @@ from .kernels import _lib
 from .kernels.layernorm import layernorm
 
 _FUSED = True
-# layernorm_before of blocks 1.. is folded into the QKV GEMM epilogue (row statistics come out of the
-# previous block's fc2 epilogue).  Per kernel it is a wash in isolation (-31 us LayerNorm, +14 us QKV,
-# +10 us fc2), but under the sustained power cap the forward is 1.3-2.3 % faster (tools/fold_ab.py:
-# 9.55 -> 9.33, 9.64 -> 9.52, 9.62 -> 9.45 ms): 12 launches and 1.9 GB of activation traffic less.
+# Both LayerNorms of a block are folded into the GEMM that consumes them: the normalisation is applied
+# per row in that GEMM's epilogue (zero-sum folded weights, packing._fold_layernorm_zero_sum) and the row
+# statistics come out of the epilogue of the GEMM that PRODUCES the row (fc2 of the previous block /
+# the patch embedding for layernorm_before, the out-proj for layernorm_after).  Measured in one process
+# under the sustained power cap (tools/fold_ab.py): 9.19 / 9.01 / 8.76 ms per forward with no fold / only
+# layernorm_before / both — 24 launches and 3.7 GB of activation traffic less per forward.
 _FOLD_LN = True
 _FOLD_LN_MLP = True    # layernorm_after -> fc1 fold (statistics from the out-proj epilogue), see set_layernorm_folding
 
@@ -58,8 +60,9 @@ def fused_enabled() -> bool:
 
 
 def set_layernorm_folding(enabled: bool, mlp: bool = True) -> None:
-    """Toggle folding of layernorm_before into the QKV GEMM epilogue (default ON, see the note at
-    _FOLD_LN; only affects the fused bf16 path).  Off = 7 launches per block instead of 6."""
+    """Toggle folding of the LayerNorms into the GEMM epilogues (default: both ON, see the note at _FOLD_LN;
+    only affects the fused bf16 path).  ``mlp=False`` keeps layernorm_after as a kernel (6 launches per
+    block), ``enabled=False`` both (7 launches per block instead of 5)."""
     global _FOLD_LN, _FOLD_LN_MLP
     _FOLD_LN = bool(enabled)
     _FOLD_LN_MLP = bool(enabled and mlp)
@@ -177,7 +180,8 @@ class Transformer(packing.PackedMixin, nn.Module):
 
         ``ln1_stats``: (M, D/128, 2) fp32 per-128-column (sum, sumsq) partials of x's rows, written by the
         previous block's last GEMM (None for the first block: layernorm_before then runs as a
-        kernel).  Returns (output, statistics of the output rows).  6 launches instead of 7."""
+        kernel).  Returns (output, statistics of the output rows).  5 launches per block (layernorm_after folded into
+        fc1 as well, the default) instead of 7."""
         att = self.attention.packed()
         mlp = self.packed()
         x = x.contiguous()
