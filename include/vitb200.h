@@ -146,7 +146,7 @@ int vt_pool_cls(const void* x, void* out, int32_t B, int32_t D, int64_t batch_st
  * step's value.  peer_out / peer_flags are HOST arrays of `world` device pointers; flags are uint32
  * counters zeroed once before the first step; `epoch` = 1, 2, 3, ... must advance by one per call on
  * every rank, all ranks must pass the same B and D, and the caller alternates between two gather
- * buffers by the parity of epoch.  world <= 16.  A peer that never arrives traps the kernel after ~10 s.
+ * buffers by the parity of epoch.  world <= 16.  A peer that never arrives traps the kernel after 120 s.
  * (New: the reference has no multi-GPU step; replaces vt_pool_cls + ncclAllGather.) */
 int vt_pool_cls_allgather(const void* x, int32_t B, int32_t D, int64_t batch_stride, int32_t dtype,
                           void* const* peer_out, uint32_t* const* peer_flags, int32_t rank, int32_t world,

@@ -411,12 +411,15 @@ pool_cls_allgather_kernel(const uint4* __restrict__ x, long long batch_stride_v,
     if (j == 0) {
       const unsigned int target = epoch * static_cast<unsigned int>(blocks_per_peer);
       const unsigned int* mine = peers.flags[rank] + p;
-      const long long t0 = clock64();
+      unsigned long long t0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
       unsigned int v;
       for (;;) {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
         if (static_cast<int>(v - target) >= 0) break;
-        if (clock64() - t0 > 20000000000LL) {   // ~10 s: a peer died; surface it as a CUDA error, not a hang
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > 120000000000ULL) {   // 120 s: a peer died; surface it as a CUDA error, not a hang
           printf("vt: pool_cls_allgather timeout rank %d waiting for rank %d (flag %u, want %u)\n", rank, p, v,
                  target);
           __trap();
