@@ -180,3 +180,36 @@ def test_gelu_polynomial_restatement_matches_exact_erf():
     want = torch.nn.functional.gelu(torch.from_numpy(x).double()).numpy()
     assert np.isfinite(got).all()
     assert np.abs(got - want).max() <= 1e-6
+
+
+@pytest.mark.parametrize("K,N", [(128, 96), (768, 320), (1280, 64)])
+def test_zero_sum_layernorm_fold_packing(K, N):
+    """packing._fold_layernorm_zero_sum (host logic of the LayerNorm -> GEMM fold, reference pair
+    layernorm.py:90-127 + matmul.py:111-156): the folded bf16 weight rows sum to ~0, no element moves by
+    more than one extra bf16 ulp, and rstd * (x @ W'^T) + b' reproduces LayerNorm -> dense as well as the
+    column-sum form does."""
+    import math
+    torch.manual_seed(K + N)
+    ln = torch.nn.LayerNorm(K, eps=1e-12)
+    with torch.no_grad():
+        ln.weight.copy_(1 + 0.2 * torch.randn(K))
+        ln.bias.copy_(0.2 * torch.randn(K))
+    w = (torch.randn(N, K) / math.sqrt(K)).bfloat16()
+    b = torch.randn(N)
+    wz, bz = packing._fold_layernorm_zero_sum(w, b, ln)
+    wf, bf, cs = packing._fold_layernorm(w, b, ln)
+    assert wz.dtype == torch.bfloat16 and torch.equal(bz, bf)
+    assert wz.double().sum(dim=1).abs().max().item() <= 2e-3 * wz.float().abs().mean().item()
+    exact = w.float() * ln.weight.detach()[None, :]
+    exact = exact - exact.mean(dim=1, keepdim=True)
+    ulp = torch.exp2(torch.floor(torch.log2(exact.abs().clamp_min(1e-30))) - 7.0)
+    assert ((wz.float() - exact).abs() <= 2.6 * ulp + 1e-12).all()     # rounding (0.5) + one move (1) + binade edges
+    x = (2.0 * torch.randn(300, K) + 0.7).bfloat16().float()
+    want = torch.nn.functional.layer_norm(x, (K,), ln.weight, ln.bias, 1e-12) @ w.float().t() + b
+    mean = x.mean(dim=1, keepdim=True)
+    rstd = (x.var(dim=1, unbiased=False, keepdim=True) + 1e-12).rsqrt()
+    got_z = rstd * (x @ wz.float().t()) + bz
+    got_c = rstd * (x @ wf.float().t()) - rstd * mean * cs + bf
+    err_z = ((got_z - want).norm() / want.norm()).item()
+    err_c = ((got_c - want).norm() / want.norm()).item()
+    assert err_z <= 1.1 * err_c + 1e-5 and err_z <= 2e-3
