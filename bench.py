@@ -5,7 +5,8 @@
 
 One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1).  A step = one forward
 of the per-GPU batch (weak scaling: the per-GPU batch is fixed) + CLS pooling + the all-gather of
-the pooled embeddings when N > 1.  Rank 0 prints ONE JSON line.
+the pooled embeddings when N > 1 (one pool + peer-store kernel over NVLink, vit/parallel.py:PeerGather;
+VT_PEER_GATHER=0 = vt_pool_cls + NCCL; `config.gather` says which ran).  Rank 0 prints ONE JSON line.
 
   value     device-resident inputs, CUDA-event timed, max over ranks
   e2e       same steps through the public API from PINNED HOST buffers: H2D of every step's pixels
