@@ -41,6 +41,20 @@ def run(rank: int, world: int, port: int, steps: int = 5) -> None:
                 assert fused.gather_impl == "peer-store kernel" and plain.gather_impl == "torch.distributed"
                 assert a.shape == b.shape == (6 * world, b.shape[1])
                 assert torch.equal(a, b), f"rank {rank} step {step}: peer-store gather differs from NCCL"
+            # class logits through the same kernel ((B, 1, num_labels) "hidden states")
+            torch.manual_seed(1)
+            clf = VIT(**configs.vit_kwargs("tiny-b"), num_labels=40).to("cuda", torch.bfloat16)
+            for p_ in clf.parameters():
+                p_.copy_(torch.randn_like(p_) * 0.05)
+            fused_l = DataParallelVIT(clf, peer_gather=True, output="logits")
+            plain_l = DataParallelVIT(clf, peer_gather=False, output="logits")
+            for step in range(3):
+                g = torch.Generator(device="cuda").manual_seed(7 * step + rank)
+                x = torch.randn(4, 3, size, size, device="cuda", generator=g).bfloat16()
+                a = fused_l(x).clone()
+                b = plain_l(x)
+                assert fused_l.gather_impl == "peer-store kernel" and a.shape == b.shape == (4 * world, 40)
+                assert torch.equal(a, b), f"rank {rank} step {step}: gathered logits differ from NCCL"
         torch.cuda.synchronize()
         dist.barrier()
         if rank == 0:

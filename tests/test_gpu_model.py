@@ -242,3 +242,28 @@ def test_peer_gather_matches_nccl_world2():
     port = s.getsockname()[1]
     s.close()
     mp.spawn(peer_gather_worker.run, args=(2, port), nprocs=2, join=True)
+
+
+def test_classifier_head_matches_hf_image_classification():
+    """Row f2: HF ViTForImageClassification(...).logits == VIT(num_labels=...).logits, weights moved by
+    transfer_pretrained_weights (source keys carry the ``vit.`` prefix, classifier.* is transposed)."""
+    from transformers import ViTConfig, ViTForImageClassification
+    from vit.utils import transfer_pretrained_weights
+    from vit.vit import VIT
+    arch = "tiny-b"
+    torch.manual_seed(5)
+    hf = ViTForImageClassification(ViTConfig(**hf_oracle.ARCHS[arch], num_labels=40)).eval()
+    with torch.no_grad():
+        hf.classifier.weight.copy_(torch.randn_like(hf.classifier.weight) * 0.1)
+        hf.classifier.bias.copy_(torch.randn_like(hf.classifier.bias) * 0.1)
+    x = hf_oracle.make_input(arch, 5)
+    with torch.no_grad():
+        want = hf(pixel_values=x).logits
+    for dtype, tol in ((torch.float32, 1e-4), (torch.bfloat16, 5e-2)):
+        model = VIT(**hf_oracle.vit_kwargs(arch), num_labels=40)
+        transfer_pretrained_weights(hf, model, verbose=False)
+        model = model.to(DEV, dtype).eval()
+        with torch.no_grad():
+            got = model.logits(x.to(DEV, dtype)).float().cpu()
+        assert got.shape == want.shape == (5, 40)
+        assert (got - want).abs().max().item() <= tol, f"{dtype}: max-abs {(got - want).abs().max().item()}"

@@ -98,6 +98,28 @@ def test_pooler_weights_load_transposed():
     assert plain.pooler is None and not any(k.startswith("pooler") for k in plain.state_dict())
 
 
+def test_classifier_head_loads_from_image_classification_model():
+    """VIT(num_labels=...): classifier.{weight,bias} are filled from HF ViTForImageClassification (source
+    keys carry the ``vit.`` prefix; the (out, in) weight lands as (in, out)); the default model has no
+    classifier and keeps the reference's state-dict keys."""
+    from transformers import ViTConfig, ViTForImageClassification
+    arch = "tiny-b"
+    torch.manual_seed(2)
+    hf = ViTForImageClassification(ViTConfig(**hf_oracle.ARCHS[arch], num_labels=24)).eval()
+    with torch.no_grad():
+        hf.classifier.weight.copy_(torch.randn_like(hf.classifier.weight))
+        hf.classifier.bias.copy_(torch.randn_like(hf.classifier.bias))
+    model = VIT(**hf_oracle.vit_kwargs(arch), num_labels=24)
+    transfer_pretrained_weights(hf, model, verbose=False)
+    assert torch.equal(model.classifier.weight, hf.classifier.weight.t())
+    assert torch.equal(model.classifier.bias, hf.classifier.bias)
+    assert torch.equal(model.layernorm.weight, hf.vit.layernorm.weight)
+    plain = VIT(**hf_oracle.vit_kwargs(arch))
+    assert plain.classifier is None and not any(k.startswith("classifier") for k in plain.state_dict())
+    with pytest.raises(AssertionError):
+        plain.logits(torch.zeros(1, 3, 64, 64))
+
+
 def test_packed_cache_invalidation():
     model = VIT(**hf_oracle.vit_kwargs("tiny-b"))
     mha = model.encoder.layer[0].attention

@@ -39,13 +39,14 @@ def map_attn_layers(source_layer_num: str, source_proj: str, source_type: str,
 
 def map_non_attn_layers(source_state_dict: dict, dest_state_dict: dict, weight_mapping: Dict) -> Dict:
     """Copy embeddings, LayerNorms and dense layers.  Dense weights ('output' / 'intermediate' /
-    'pooler' in the destination name) are transposed because HF stores (out, in) and this tree stores
-    (in, out).  'pooler.*' only exists in the destination for ``VIT(add_pooling_layer=True)``; the
+    'pooler' / 'classifier' in the destination name) are transposed because HF stores (out, in) and this
+    tree stores (in, out).  'pooler.*' only exists in the destination for ``VIT(add_pooling_layer=True)``; the
     reference maps the key (utils.py:63-64) and always skips it."""
     for src_name, tensor in source_state_dict.items():
         dst_name = weight_mapping.get(src_name)
         if not dst_name or dst_name not in dest_state_dict:
             continue
-        dense = ('output' in dst_name) or ('intermediate' in dst_name) or ('pooler' in dst_name)
+        dense = ('output' in dst_name) or ('intermediate' in dst_name) or ('pooler' in dst_name) \
+            or ('classifier' in dst_name)
         dest_state_dict[dst_name] = tensor.t().clone() if (dense and tensor.dim() == 2) else tensor.clone()
     return dest_state_dict

@@ -88,7 +88,7 @@ class PeerGather:
         assert hidden.is_cuda and hidden.dim() == 3, f"Expected CUDA (B, N, D) hidden states, provided: {tuple(hidden.shape)}"
         assert hidden.shape[0] == self.batch_local and hidden.shape[2] == self.dim and hidden.dtype == self.dtype, \
             f"PeerGather was built for ({self.batch_local}, *, {self.dim}) {self.dtype}, provided: {tuple(hidden.shape)} {hidden.dtype}"
-        assert hidden.stride(2) == 1 and hidden.stride(1) == self.dim
+        assert hidden.stride(2) == 1 and hidden.stride(0) % 8 == 0
         self.epoch += 1
         parity = self.epoch & 1
         _lib = self._lib
@@ -103,14 +103,19 @@ class DataParallelVIT(torch.nn.Module):
     """Wraps a replicated ``VIT``: each rank runs its slice of the global batch and all ranks receive
     the gathered (B, D) pooled embeddings."""
 
-    def __init__(self, model: torch.nn.Module, group=None, peer_gather: Optional[bool] = None):
-        """``peer_gather``: None = use the fused pool + peer-store kernel whenever it applies (CUDA,
+    def __init__(self, model: torch.nn.Module, group=None, peer_gather: Optional[bool] = None,
+                 output: str = "pooled"):
+        """``output``: "pooled" gathers the CLS embeddings (B, D); "logits" gathers the class logits
+        (B, num_labels) of a model built with a classifier head (``VIT(num_labels=...)``).
+        ``peer_gather``: None = use the fused pool + peer-store kernel whenever it applies (CUDA,
         NCCL group, equal shards, symmetric memory available; VT_PEER_GATHER=0 disables), True =
         require it, False = always all-gather through torch.distributed."""
         super().__init__()
         self.model = model
         self.group = group
         self.peer_gather = peer_gather
+        assert output in ("pooled", "logits"), f"output must be 'pooled' or 'logits', provided: {output}"
+        self.output = output
         self._peer = None          # PeerGather, built on first use for one (B_local, D, dtype)
         self._peer_failed = False
         self.gather_impl = "none"  # what the last forward used: "peer-store kernel" | "torch.distributed" | "none"
@@ -127,8 +132,8 @@ class DataParallelVIT(torch.nn.Module):
         return shard_bounds(global_batch, self.world_size, self.rank)
 
     def forward_local(self, x_local: torch.Tensor) -> torch.Tensor:
-        """Pooled embeddings of this rank's images, (B_local, D); no communication."""
-        return self.model.pooled(x_local)
+        """Pooled embeddings (or logits) of this rank's images, (B_local, D | num_labels); no communication."""
+        return self.model.logits(x_local) if self.output == "logits" else self.model.pooled(x_local)
 
     def forward(self, x_local: torch.Tensor, global_batch: Optional[int] = None) -> torch.Tensor:
         """x_local: this rank's shard of the global batch (as laid out by ``local_slice``).
@@ -139,7 +144,10 @@ class DataParallelVIT(torch.nn.Module):
         if global_batch is None:
             global_batch = x_local.shape[0] * world
         if self._wants_peer(x_local, global_batch):
-            hidden = self.model.forward_uint8(x_local) if x_local.dtype == torch.uint8 else self.model(x_local)
+            if self.output == "logits":
+                hidden = self.model.logits(x_local).unsqueeze(1)      # (B_local, 1, num_labels): "CLS row" = the logits
+            else:
+                hidden = self.model.forward_uint8(x_local) if x_local.dtype == torch.uint8 else self.model(x_local)
             peer = self._peer_for(hidden)
             if peer is not None:
                 self.gather_impl = "peer-store kernel"
@@ -160,6 +168,8 @@ class DataParallelVIT(torch.nn.Module):
             return False
         ok = x_local.is_cuda and global_batch == x_local.shape[0] * self.world_size and x_local.shape[0] > 0 \
             and dist.get_backend(self.group) == "nccl"
+        if ok and self.output == "logits":
+            ok = self.model.classifier.weight.shape[1] % 8 == 0      # 16-byte rows for the vector stores
         if self.peer_gather is True:
             assert ok, "peer_gather=True needs CUDA inputs, an NCCL group and equal shards"
         return ok

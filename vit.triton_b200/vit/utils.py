@@ -38,6 +38,8 @@ def _dense_mapping(num_layers: int) -> dict:
         'layernorm.bias': 'layernorm.bias',
         'pooler.dense.weight': 'pooler.dense.weight',
         'pooler.dense.bias': 'pooler.dense.bias',
+        'classifier.weight': 'classifier.weight',     # ViTForImageClassification head, VIT(num_labels=...)
+        'classifier.bias': 'classifier.bias',
     }
     for i in range(num_layers):
         pre = f'encoder.layer.{i}.'

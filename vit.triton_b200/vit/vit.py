@@ -317,6 +317,7 @@ class VIT(nn.Module):
         num_layers: int,
         mlp_dim: Optional[int] = None,
         add_pooling_layer: bool = False,
+        num_labels: Optional[int] = None,
     ):
         super().__init__()
         assert height == width, "Height and width should be the same"
@@ -344,6 +345,9 @@ class VIT(nn.Module):
         self.layernorm = LayerNormTriton(dim=self.hidden_dim, eps=1e-12)
         # optional HF pooler (tanh(dense(CLS))): state-dict keys pooler.dense.{weight,bias}
         self.pooler = Pooler(self.hidden_dim) if add_pooling_layer else None
+        # optional HF ViTForImageClassification head (Linear on the CLS row of the final hidden states):
+        # state-dict keys classifier.{weight,bias}
+        self.classifier = LinearWithBias(self.hidden_dim, num_labels) if num_labels else None
 
     @property
     def device(self) -> torch.device:
@@ -393,6 +397,13 @@ class VIT(nn.Module):
         assert self.pooler is not None, "Model was built without add_pooling_layer=True"
         hidden = self.forward_uint8(x) if x.dtype == torch.uint8 else self.forward(x)
         return self.pooler(hidden)
+
+    def logits(self, x) -> torch.Tensor:
+        """Class logits (B, num_labels) = classifier(final hidden states[:, 0]) — HF
+        ``ViTForImageClassification(...).logits``; needs ``VIT(..., num_labels=...)``."""
+        assert self.classifier is not None, "VIT was built without a classifier head (num_labels)"
+        cls = self.pooled(x).unsqueeze(1)                  # (B, 1, D)
+        return self.classifier(cls)[:, 0, :]
 
     def pooled(self, x) -> torch.Tensor:
         """CLS row of the final hidden states, (B, D): the tensor the data-parallel wrapper gathers.
