@@ -65,14 +65,18 @@ int vt_gemm_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, void* 
                  int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream);
 
 /* K1 with LayerNorm folded into the epilogue and/or row statistics emitted for the next fold (bf16 out).
- *   rowstats != NULL (with colsum): A is the UN-normalised activation; row m's (sum, sumsq) over its
- *     ln_dim elements is given as ln_dim/128 partial pairs rowstats[(m*(ln_dim/128) + i)*2 .. +1]
- *     (summed in index order: bit-reproducible); ln_dim % 128 == 0; Bt must carry gamma
+ *   rowstats != NULL (with colsum): A is the UN-normalised activation; row m's statistics are given as
+ *     ln_dim/128 partial pairs rowstats[(m*(ln_dim/128) + i)*2 .. +1] = (sum, M2) of the i-th group of 128
+ *     elements, M2 = sum of squares about the GROUP's mean; the groups are merged the Chan / Welford way
+ *     (in index order: bit-reproducible), so the variance is a sum of centred squares like the reference's
+ *     two-pass kernel (vit/kernels/layernorm.py:51-85) even for rows with |mean| >> std; a row whose
+ *     variance is exactly 0 yields out = bias_n (= LN's beta through the dense layer).
+ *     ln_dim % 128 == 0; Bt must carry gamma
  *     (Bt[n,k] = W[n,k] * gamma[k]), bias must carry beta (bias[n] + sum_k beta[k] W[n,k]) and
  *     colsum[n] = sum_k Bt[n,k]:   out = rstd_m * acc - rstd_m * mean_m * colsum_n + bias_n  (then GELU).
  *     colsum == NULL: the rows of Bt sum to zero (Bt[n,k] = W[n,k]*gamma[k] - mean_k(W[n,k]*gamma[k])), the
  *     mean term is then part of acc and   out = rstd_m * acc + bias_n.
- *   stats_out != NULL (needs residual, N % 128 == 0): writes the (sum, sumsq) of every 128-column group
+ *   stats_out != NULL (needs residual, N % 128 == 0): writes the (sum, M2) of every 128-column group
  *     of every output row to stats_out[(m*(N/128) + group)*2 .. +1] — the rowstats layout above.
  * Replaces layernorm_triton (vit/kernels/layernorm.py:90-127) + matmul_triton for the
  * LN -> dense pairs of Transformer.forward (vit/vit.py:133-144). */
@@ -80,6 +84,19 @@ int vt_gemm_bf16_ln(const void* A, int64_t lda, const void* Bt, int64_t ldb, voi
                     const float* bias, const void* residual, int64_t ldr, int32_t M, int32_t N, int32_t K,
                     int32_t gelu, const float* rowstats, const float* colsum, int32_t ln_dim, float ln_eps,
                     float* stats_out, void* stream);
+
+/* Pack-time fold of a LayerNorm (gamma, beta: f32 [K]) into the dense layer that consumes it, producing the
+ * operands vt_gemm_bf16_ln expects.  w, w_out: bf16 [N, K] K-major (row strides ldw / ldo in elements);
+ * bias (f32 [N], nullable) -> bias_out[n] = bias[n] + sum_k w[n,k] * beta[k].
+ *   zero_sum == 0: w_out[n,k] = bf16(w[n,k] * gamma[k]), colsum_out[n] = sum_k w_out[n,k]  (f32 [N])
+ *   zero_sum != 0: every row of w * gamma is shifted by its own mean before rounding and the rounding
+ *     residue of the row sum is cancelled by re-rounding the elements nearest to a tie (each element moves
+ *     by at most one bf16 ulp), so sum_k w_out[n,k] ~ 1e-6 and the GEMM needs no colsum; colsum_out may be
+ *     NULL (when given it receives the remaining row sums).
+ * Deterministic.  Replaces nothing in the reference (it has no fused LayerNorm); it is what lets
+ * layernorm_triton (vit/kernels/layernorm.py:90-127) disappear into matmul_triton's epilogue. */
+int vt_ln_fold(const void* w, int64_t ldw, const float* bias, const float* gamma, const float* beta, void* w_out,
+               int64_t ldo, float* bias_out, float* colsum_out, int32_t N, int32_t K, int32_t zero_sum, void* stream);
 
 /* Generic strided batched GEMM on the FP32 pipe (exact-fp32 path and odd shapes):
  *   C[z] = scale * act(A[z] . B[z] + bias),  z = zo * batch_inner + zi
@@ -111,7 +128,7 @@ int vt_patch_embed(const void* pixels, int32_t pix_dtype, const void* w, int64_t
                    const float* posb, void* out, int32_t out_dtype, int32_t B, int32_t C, int32_t S,
                    int32_t P, int32_t D, void* stream);
 
-/* The same, also writing the (sum, sumsq) of every 128-column group of every output row (CLS rows
+/* The same, also writing the (sum, M2 about the group mean) of every 128-column group of every output row (CLS rows
  * included) to stats_out[(row*(D/128) + group)*2 .. +1] — the rowstats layout of vt_gemm_bf16_ln, so the
  * first block's layernorm_before folds into its QKV GEMM too.  D % 128 == 0. */
 int vt_patch_embed_stats(const void* pixels, int32_t pix_dtype, const void* w, int64_t ldw,

@@ -341,7 +341,7 @@ def test_patch_embed_fused(S, P, D, B, pix_dtype):
         assert torch.equal(again, got)
         wc = want.reshape(B * (n + 1), D // 128, 128)
         assert torch.allclose(stats[..., 0], wc.sum(-1), rtol=1e-3, atol=2e-2)
-        assert torch.allclose(stats[..., 1], (wc * wc).sum(-1), rtol=1e-3, atol=2e-2)
+        assert torch.allclose(stats[..., 1], (wc - wc.mean(-1, keepdim=True)).pow(2).sum(-1), rtol=1e-3, atol=2e-2)
 
 
 @pytest.mark.parametrize("S,P,D,B", [(224, 16, 768, 3), (64, 16, 128, 5), (56, 14, 160, 2), (224, 14, 1280, 1), (96, 32, 64, 2)])
@@ -380,33 +380,181 @@ def test_pool_cls():
 
 
 # ------------------------------------------------------------------------------- LayerNorm folded into the GEMM
-@pytest.mark.parametrize("M,K,N", [(197 * 5, 768, 2304), (300, 128, 512), (129, 1280, 264), (260, 384, 640), (70, 1536, 256)])
-@pytest.mark.parametrize("gelu", [False, True])
-@pytest.mark.parametrize("zero_sum", [False, True])
-def test_gemm_layernorm_fold(M, K, N, gelu, zero_sum):
-    """vt_gemm_bf16_ln == dense(LayerNorm(x)) with the normalisation applied in the epilogue."""
-    from vit import packing
-    x = (2.0 * torch.randn(1, M, K, device=dev()) + 0.7).bfloat16()
+def _group_stats(xf):
+    """(M, K) fp32 -> (M, K/128, 2): (sum, M2 about the group's own mean) — the rowstats layout of vt_gemm_bf16_ln."""
+    M, K = xf.shape
+    xc = xf.view(M, K // 128, 128).double()
+    m2 = ((xc - xc.mean(-1, keepdim=True)) ** 2).sum(-1)
+    return torch.stack([xc.sum(-1), m2], dim=2).float().contiguous()
+
+
+def _ln_module(K):
     ln = torch.nn.LayerNorm(K, eps=1e-12).to(dev())
     with torch.no_grad():
         ln.weight.copy_(1 + 0.2 * torch.randn(K, device=dev()))
         ln.bias.copy_(0.2 * torch.randn(K, device=dev()))
+    return ln
+
+
+@pytest.mark.parametrize("M,K,N", [(197 * 5, 768, 2304), (300, 128, 512), (129, 1280, 264), (260, 384, 640), (70, 1536, 256)])
+@pytest.mark.parametrize("gelu", [False, True])
+@pytest.mark.parametrize("zero_sum", [False, True])
+def test_gemm_layernorm_fold(M, K, N, gelu, zero_sum):
+    """vt_gemm_bf16_ln == dense(LayerNorm(x)) with the normalisation applied in the epilogue; the folded
+    operands come from the pack kernel (vt_ln_fold)."""
+    from vit import packing
+    x = (2.0 * torch.randn(1, M, K, device=dev()) + 0.7).bfloat16()
+    ln = _ln_module(K)
     w_nk = (torch.randn(N, K, device=dev()) / math.sqrt(K)).bfloat16()
     bias = torch.randn(N, device=dev())
+    w_fold, b_fold, colsum = packing.fold_layernorm(w_nk, bias, ln, zero_sum=zero_sum)
     if zero_sum:      # mean term inside the weights (rows sum to zero), no column-sum operand
-        w_fold, b_fold = packing._fold_layernorm_zero_sum(w_nk, bias, ln)
-        colsum = None
+        assert colsum is None
         assert w_fold.double().sum(dim=1).abs().max().item() <= 2e-3 * w_fold.float().abs().mean().item()
-    else:
-        w_fold, b_fold, colsum = packing._fold_layernorm(w_nk, bias, ln)
     xf = x.float()[0]
-    xc = xf.view(M, K // 128, 128)
-    stats = torch.stack([xc.sum(-1), (xc * xc).sum(-1)], dim=2).contiguous()      # (M, K/128, 2) partials
-    got = packing.linear_ln(x, w_fold, b_fold, colsum, stats, 1e-12, gelu=gelu)
+    got = packing.linear_ln(x, w_fold, b_fold, colsum, _group_stats(xf), 1e-12, gelu=gelu)
     want = F.layer_norm(xf, (K,), ln.weight, ln.bias, 1e-12) @ w_nk.float().t() + bias
     if gelu:
         want = F.gelu(want)
     assert rel_err(got[0], want) <= 2 ** -7, f"rel err {rel_err(got[0], want)}"
+
+
+@pytest.mark.parametrize("K,N", [(128, 96), (768, 2304), (1280, 520), (5120, 128)])
+@pytest.mark.parametrize("zero_sum", [False, True])
+def test_ln_fold_kernel_matches_restatement(K, N, zero_sum):
+    """vt_ln_fold (csrc/ln_fold.cu) against the torch restatement of the same algorithm
+    (oracle/fold_restatement.py): identical bias, weights identical up to tie-breaking of equal prices,
+    row sums at the 1e-6 level, no element more than one extra ulp away from its exact value."""
+    from oracle import fold_restatement
+    from vit import packing
+    torch.manual_seed(K + N)
+    ln = _ln_module(K)
+    w_nk = (torch.randn(N, K, device=dev()) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=dev())
+    w_fold, b_fold, colsum = packing.fold_layernorm(w_nk, bias, ln, zero_sum=zero_sum)
+    again = packing.fold_layernorm(w_nk, bias, ln, zero_sum=zero_sum)
+    assert torch.equal(w_fold, again[0]) and torch.equal(b_fold, again[1])        # deterministic
+    if not zero_sum:
+        w_ref, b_ref, c_ref = fold_restatement.fold_layernorm_colsum(w_nk, bias, ln)
+        assert torch.equal(w_fold, w_ref)
+        assert torch.allclose(b_fold, b_ref, rtol=1e-5, atol=1e-5)
+        assert torch.allclose(colsum, w_fold.double().sum(dim=1).float(), rtol=0, atol=1e-6)
+        return
+    w_ref, b_ref = fold_restatement.fold_layernorm_zero_sum(w_nk, bias, ln)
+    assert torch.allclose(b_fold, b_ref, rtol=1e-5, atol=1e-5)
+    scale = w_fold.float().abs().mean().item()
+    assert w_fold.double().sum(dim=1).abs().max().item() <= 2e-3 * scale
+    assert w_fold.double().sum(dim=1).abs().max().item() <= 4 * w_ref.double().sum(dim=1).abs().max().item() + 1e-5 * scale
+    exact = w_nk.float() * ln.weight.detach()[None, :]
+    exact = exact - exact.mean(dim=1, keepdim=True)
+    ulp = torch.exp2(torch.floor(torch.log2(exact.abs().clamp_min(1e-30))) - 7.0)
+    assert ((w_fold.float() - exact).abs() <= 2.6 * ulp + 1e-12).all()
+    # the two implementations pick (almost) the same elements: added squared error within 10 %
+    e_k = (w_fold.float() - exact).pow(2).sum().item()
+    e_r = (w_ref.float() - exact).pow(2).sum().item()
+    assert e_k <= 1.1 * e_r + 1e-12, (e_k, e_r)
+    assert (w_fold != w_ref).float().mean().item() <= 0.02
+
+
+def _stats_of(x):
+    """Row statistics of x (1, M, K) bf16 as the GEMM epilogue writes them: out = 0 @ W^T + 0 + x."""
+    from vit import packing
+    _, M, K = x.shape
+    zeros = torch.zeros(1, M, 64, device=x.device, dtype=torch.bfloat16)
+    w0 = torch.zeros(K, 64, device=x.device, dtype=torch.bfloat16)
+    b0 = torch.zeros(K, device=x.device)
+    stats = torch.full((M, K // 128, 2), float("nan"), device=x.device)
+    out = packing.linear_res_stats(zeros, w0, b0, x, stats)
+    assert torch.equal(out, x)
+    return stats
+
+
+OUTLIER_CASES = ["massive_channels", "large_mean_100", "large_mean_1000", "near_constant", "constant", "mixed"]
+
+
+def _outlier_rows(case, M, K):
+    g = torch.Generator(device="cpu").manual_seed(sum(map(ord, case)))
+    x = torch.randn(M, K, generator=g)
+    if case == "massive_channels":          # a few channels at +-50..200 in every row (real ViT checkpoints)
+        for ch, v in ((3, 60.0), (K // 2 + 1, -120.0), (K - 5, 200.0), (130 % K, -50.0)):
+            x[:, ch] = v * (1 + 0.05 * torch.randn(M, generator=g))
+    elif case == "large_mean_100":          # |mean| / std = 100
+        x = 0.5 * x + 50.0
+    elif case == "large_mean_1000":         # |mean| / std = 1000: one-pass E[x^2] - mean^2 has no digits left
+        x = 0.1 * x - 100.0
+    elif case == "near_constant":           # spread of a few bf16 ulps around a constant
+        x = 1.0 + 0.01 * x
+    elif case == "constant":                # variance exactly 0: LN(x) = beta
+        x = torch.full((M, K), 3.25)
+        x[M // 2:] = 0.0
+    elif case == "mixed":                   # every row different: offsets, scales and planted channels
+        x = x * torch.logspace(-2, 2, M)[:, None] + torch.linspace(-300, 300, M)[:, None]
+        x[::3, 7] = 1000.0
+    return x
+
+
+@pytest.mark.parametrize("case", OUTLIER_CASES)
+@pytest.mark.parametrize("K,N", [(768, 512), (1280, 264)])
+@pytest.mark.parametrize("gelu", [False, True])
+def test_gemm_layernorm_fold_outliers(case, K, N, gelu):
+    """The LayerNorm fold on the activations real checkpoints produce and the benign tests do not: massive
+    channels, rows with |mean| >> std, near-constant and constant rows.  Statistics come from the GEMM
+    epilogue itself (vt_gemm_bf16_ln stats_out); the oracle is F.layer_norm -> dense in fp32 on the same
+    bf16 inputs (reference: centred two-pass variance, vit/kernels/layernorm.py:51-85)."""
+    from vit import packing
+    M = 333
+    torch.manual_seed(11)
+    x = _outlier_rows(case, M, K).to(dev()).bfloat16()[None]
+    ln = _ln_module(K)
+    w_nk = (torch.randn(N, K, device=dev()) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=dev())
+    w_fold, b_fold, _ = packing.fold_layernorm(w_nk, bias, ln)
+    stats = _stats_of(x)
+    xf = x.float()[0]
+    ref_stats = _group_stats(xf)
+    assert torch.allclose(stats[..., 0], ref_stats[..., 0], rtol=1e-5, atol=1e-3)
+    assert torch.allclose(stats[..., 1], ref_stats[..., 1], rtol=1e-3, atol=1e-6), \
+        f"M2 max rel err {((stats[..., 1] - ref_stats[..., 1]).abs() / ref_stats[..., 1].clamp_min(1e-20)).max().item()}"
+    got = packing.linear_ln(x, w_fold, b_fold, None, stats, 1e-12, gelu=gelu).float()[0]
+    want = F.layer_norm(xf.double(), (K,), ln.weight.double(), ln.bias.double(), 1e-12).float() @ w_nk.float().t() + bias
+    if gelu:
+        want = F.gelu(want)
+    assert torch.isfinite(got).all()
+    # per row: the folded result is as good as bf16 rounding of the exact result allows
+    row_err = (got - want).norm(dim=1) / want.norm(dim=1).clamp_min(1e-6)
+    assert row_err.max().item() <= 2 ** -6, f"{case}: worst row rel err {row_err.max().item()} (row {row_err.argmax().item()})"
+    assert rel_err(got, want) <= 2 ** -7, f"{case}: rel err {rel_err(got, want)}"
+
+
+@pytest.mark.parametrize("case", ["massive_channels", "large_mean_100", "mixed"])
+def test_patch_embed_stats_outliers(case):
+    """Row statistics written by the patch-embedding epilogue when the position / bias table carries large
+    offsets and planted channels (the rows of block 0's folded layernorm_before)."""
+    from vit.vit import Embeddings
+    torch.manual_seed(5)
+    P, S, D, B = 16, 64, 256, 3
+    n = (S // P) ** 2
+    emb = Embeddings(P, n, 3 * P * P, D).to(dev(), torch.bfloat16)
+    with torch.no_grad():
+        emb.projection.weight.copy_(torch.randn_like(emb.projection.weight) * 0.02)
+        emb.projection.bias.copy_(torch.randn_like(emb.projection.bias) * 0.02)
+        emb.cls_token.copy_(torch.randn_like(emb.cls_token))
+        pos = _outlier_rows(case, n + 1, D).to(dev())
+        emb.position_embeddings.copy_(pos[None].bfloat16())
+    x = torch.randn(B, 3, S, S, device=dev()).bfloat16()
+    plain = emb(x)
+    stats = torch.full((B * (n + 1), D // 128, 2), float("nan"), device=dev())
+    again = emb(x, stats)
+    assert torch.equal(plain, again)
+    # the kernel's statistics are those of the fp32 values BEFORE the bf16 rounding of the output
+    pk = emb.packed()
+    from vit.kernels.patching import patching
+    patches = patching(x, P).float()                                     # (B, n, K)
+    tok = patches @ pk.w[:, :pk.K].float().t()                           # (B, n, D)
+    full = torch.cat([torch.zeros(B, 1, D, device=dev()), tok], dim=1) + pk.posb[None]
+    ref = _group_stats(full.reshape(B * (n + 1), D))
+    assert torch.allclose(stats[..., 0], ref[..., 0], rtol=1e-4, atol=5e-2)
+    assert torch.allclose(stats[..., 1], ref[..., 1], rtol=2e-3, atol=1e-3)
 
 
 def test_gemm_row_stats_output():
@@ -422,7 +570,7 @@ def test_gemm_row_stats_output():
     assert rel_err(got[0], want) <= 2 ** -7
     wc = want.view(M, N // 128, 128)
     assert torch.allclose(stats[..., 0], wc.sum(-1), rtol=1e-3, atol=2e-2)
-    assert torch.allclose(stats[..., 1], (wc * wc).sum(-1), rtol=1e-3, atol=2e-2)
+    assert torch.allclose(stats[..., 1], (wc - wc.mean(-1, keepdim=True)).pow(2).sum(-1), rtol=1e-3, atol=2e-2)
     again = torch.empty_like(stats)
     packing.linear_res_stats(x, w_nk, bias, res, again)
     assert torch.equal(stats, again)          # no atomics: bit-reproducible

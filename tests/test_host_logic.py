@@ -206,8 +206,9 @@ def test_gelu_polynomial_restatement_matches_exact_erf():
 
 @pytest.mark.parametrize("K,N", [(128, 96), (768, 320), (1280, 64)])
 def test_zero_sum_layernorm_fold_packing(K, N):
-    """packing._fold_layernorm_zero_sum (host logic of the LayerNorm -> GEMM fold, reference pair
-    layernorm.py:90-127 + matmul.py:111-156): the folded bf16 weight rows sum to ~0, no element moves by
+    """The arithmetic of the LayerNorm -> GEMM fold (csrc/ln_fold.cu restated in torch,
+    oracle/fold_restatement.py; reference pair layernorm.py:90-127 + matmul.py:111-156; the GPU tests compare
+    the kernel with this restatement): the folded bf16 weight rows sum to ~0, no element moves by
     more than one extra bf16 ulp, and rstd * (x @ W'^T) + b' reproduces LayerNorm -> dense as well as the
     column-sum form does."""
     import math
@@ -218,8 +219,9 @@ def test_zero_sum_layernorm_fold_packing(K, N):
         ln.bias.copy_(0.2 * torch.randn(K))
     w = (torch.randn(N, K) / math.sqrt(K)).bfloat16()
     b = torch.randn(N)
-    wz, bz = packing._fold_layernorm_zero_sum(w, b, ln)
-    wf, bf, cs = packing._fold_layernorm(w, b, ln)
+    from oracle import fold_restatement
+    wz, bz = fold_restatement.fold_layernorm_zero_sum(w, b, ln)
+    wf, bf, cs = fold_restatement.fold_layernorm_colsum(w, b, ln)
     assert wz.dtype == torch.bfloat16 and torch.equal(bz, bf)
     assert wz.double().sum(dim=1).abs().max().item() <= 2e-3 * wz.float().abs().mean().item()
     exact = w.float() * ln.weight.detach()[None, :]

@@ -41,6 +41,8 @@ int attn5mb_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, 
 int patch_embed_tcgen05(const void*, int, const void*, long long, const float*, void*, int, float*, int,
                         int, int, int, int, cudaStream_t);
 int patching(const void*, void*, int, int, int, int, int, int, cudaStream_t);
+int ln_fold(const void*, long long, const float*, const float*, const float*, void*, long long, float*, float*, int,
+            int, int, cudaStream_t);
 int embed_finalize(void*, const void*, const void*, int, int, int, int, cudaStream_t);
 int conv2d_nchw(const void*, const void*, const void*, void*, int, int, int, int, int, int, int,
                 int, cudaStream_t);
@@ -188,6 +190,11 @@ int vt_patch_embed_stats(const void* pixels, int32_t pix_dtype, const void* w, i
                          int32_t C, int32_t S_, int32_t P, int32_t D, void* stream) {
   return vt::patch_embed_tcgen05(pixels, pix_dtype, w, ldw, posb, out, out_dtype, stats_out, B, C, S_, P, D,
                                  S(stream));
+}
+
+int vt_ln_fold(const void* w, int64_t ldw, const float* bias, const float* gamma, const float* beta, void* w_out,
+               int64_t ldo, float* bias_out, float* colsum_out, int32_t N, int32_t K, int32_t zero_sum, void* stream) {
+  return vt::ln_fold(w, ldw, bias, gamma, beta, w_out, ldo, bias_out, colsum_out, N, K, zero_sum, S(stream));
 }
 
 int vt_patching(const void* image, void* out, int32_t B, int32_t C, int32_t H, int32_t W, int32_t P,

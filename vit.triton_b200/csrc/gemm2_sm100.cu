@@ -81,15 +81,15 @@ struct Gemm2Params {
   int reverse;                    // walk the row tiles from the last to the first (L2 reuse, see api.cu)
   const float* bias;
   // LayerNorm folded into the epilogue (EPI_LNF): out = rstd_m * acc + (-rstd_m * mean_m) * colsum_n + bias_n
-  // with (sum, sumsq) of the A row given as ln_parts = ln_dim / 128 partial pairs
+  // with (sum, M2) of the A row given as ln_parts = ln_dim / 128 partial pairs (M2 about the group mean)
   // rowstats[(m*ln_parts + i)*2 .. +1]
   const float* rowstats;
   const float* colsum;
   float ln_inv_dim, ln_eps;
   int ln_parts;
-  // EPI_STATS: write (sum, sumsq) of every 128-column group (one epilogue warp's share of a tile) of
-  // every output row to stats_out[(m * (N/128) + group) * 2 .. +1]: no atomics, so results are
-  // bit-reproducible
+  // EPI_STATS: write (sum, M2 = sum of squares about the group mean) of every 128-column group (one
+  // epilogue warp's share of a tile) of every output row to stats_out[(m * (N/128) + group) * 2 .. +1]:
+  // no atomics, so results are bit-reproducible
   float* stats_out;
   long long* dbg;   // optional per-CTA cycle counters (vt_debug_set_buffer); null in production
   // Epilogue pacing (see the epilogue): cycles between the start slots of the tile's store bursts,
@@ -399,31 +399,47 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 
       float ln_a = 1.f, ln_b = 0.f;
       if (EPI & EPI_LNF) {
+        // Row statistics arrive as per-128-column (sum, M2) partials, M2 = sum of squares about the
+        // group's OWN mean; they are merged the Chan / Welford way (sum of the M2 plus 128 * squared
+        // distance of every group mean from the row mean), so the variance is a sum of non-negative
+        // centred terms like the reference's two-pass form (vit/kernels/layernorm.py:51-85) and never a
+        // difference of two large numbers (rows with |mean| >> std, massive-activation channels).
         const int row = row0 + lane;
         if (row < p.M) {
-          float sx = 0.f, sq = 0.f;
+          float sx = 0.f, m2 = 0.f;
           if (rs_fast) {                            // fixed order: deterministic
+#pragma unroll
+            for (int i = 0; i < kRsRegs; ++i)
+              if (2 * i < p.ln_parts) sx += rsn[i].x + rsn[i].z;
+            const float mean_f = sx * p.ln_inv_dim;
 #pragma unroll
             for (int i = 0; i < kRsRegs; ++i) {
               if (2 * i < p.ln_parts) {
-                sx += rsn[i].x;
-                sq += rsn[i].y;
-                sx += rsn[i].z;
-                sq += rsn[i].w;
+                const float d0 = fmaf(rsn[i].x, 1.0f / 128.0f, -mean_f);
+                const float d1 = fmaf(rsn[i].z, 1.0f / 128.0f, -mean_f);
+                m2 += rsn[i].y + rsn[i].w;
+                m2 = fmaf(128.0f * d0, d0, m2);
+                m2 = fmaf(128.0f * d1, d1, m2);
               }
             }
           } else {
             const float2* parts =
                 reinterpret_cast<const float2*>(p.rowstats) + static_cast<long long>(row) * p.ln_parts;
+            for (int i = 0; i < p.ln_parts; ++i) sx += __ldg(parts + i).x;
+            const float mean_s = sx * p.ln_inv_dim;
             for (int i = 0; i < p.ln_parts; ++i) {
               const float2 st = __ldg(parts + i);
-              sx += st.x;
-              sq += st.y;
+              const float d = fmaf(st.x, 1.0f / 128.0f, -mean_s);
+              m2 += st.y;
+              m2 = fmaf(128.0f * d, d, m2);
             }
           }
           const float mean = sx * p.ln_inv_dim;
-          const float var = fmaxf(sq * p.ln_inv_dim - mean * mean, 0.f);
-          ln_a = rsqrtf(var + p.ln_eps);
+          const float var = m2 * p.ln_inv_dim;
+          // var == 0 exactly: every element equals the mean, LN(x) = beta whatever rstd is (the reference
+          // multiplies rstd by x - mean = 0); rstd = 1/sqrt(eps) would only amplify the rounding residue
+          // of the zero-sum weight rows
+          ln_a = var > 0.f ? rsqrtf(var + p.ln_eps) : 0.f;
           ln_b = -ln_a * mean;
         }
       }
@@ -446,7 +462,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const long long pace_t0 = paced ? clock64() + q * p.pace_q : 0;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + cgrp * kColsPerWarp;
 
-      float2 st_sum2 = make_float2(0.f, 0.f), st_sq2 = make_float2(0.f, 0.f);   // even / odd columns
+      // EPI_STATS: sums of (x - pivot) and (x - pivot)^2 over this warp's 128 columns of the row, even / odd
+      // columns apart; the pivot is the row's first value in the group, so the squares stay of the order of
+      // the spread inside the group and M2 = Q - S^2 / 128 loses nothing to cancellation
+      float2 st_sum2 = make_float2(0.f, 0.f), st_sq2 = make_float2(0.f, 0.f), st_npiv2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
         const int col = col0 + c * kChunkCols;
@@ -538,10 +557,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
               for (int q = 0; q < 4; ++q) v[q] = gelu_epi2(v[q]);
             }
             if (EPI & EPI_STATS) {
+              if (c == 0 && hh == 0 && jj == 0) st_npiv2 = make_float2(-v[0].x, -v[0].x);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                st_sum2 = __fadd2_rn(st_sum2, v[q]);
-                st_sq2 = __ffma2_rn(v[q], v[q], st_sq2);
+                const float2 d = __fadd2_rn(v[q], st_npiv2);
+                st_sum2 = __fadd2_rn(st_sum2, d);
+                st_sq2 = __ffma2_rn(d, d, st_sq2);
               }
             }
             uint4 o4;
@@ -557,7 +578,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           if (col0 < p.N && row < p.M) {          // N % 128 == 0: a warp's two chunks are both in or both out
             float2* dst = reinterpret_cast<float2*>(p.stats_out) +
                           static_cast<long long>(row) * (p.N >> 7) + (col0 >> 7);
-            *dst = make_float2(st_sum2.x + st_sum2.y, st_sq2.x + st_sq2.y);
+            const float s_sh = st_sum2.x + st_sum2.y, q_sh = st_sq2.x + st_sq2.y;
+            *dst = make_float2(fmaf(-128.0f, st_npiv2.x, s_sh), fmaxf(fmaf(-s_sh * (1.0f / 128.0f), s_sh, q_sh), 0.f));
           }
         }
         if (live) {

@@ -53,7 +53,7 @@ struct PatchParams {
   const float* posb;    // [n_patches + 1, D] fp32: pos + (cls | conv bias)
   void* out;            // [B, n_patches + 1, D]
   int out_f32;
-  // optional: (sum, sumsq) of every 128-column group of every output row, [(B * (n_patches + 1)), D / 128, 2]
+  // optional: (sum, M2 about the group mean) of every 128-column group of every output row, [(B * (n_patches + 1)), D / 128, 2]
   // — the row statistics the LayerNorm folded into the first QKV GEMM consumes (gemm2_sm100.cu)
   float* stats;
 };
@@ -305,7 +305,8 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const Patc
       }
     };
     float4 pb_cur[4], pb_nxt[4];
-    float2 st_sum2 = make_float2(0.f, 0.f), st_sq2 = make_float2(0.f, 0.f);   // this warp's 128 columns of the row
+    // this warp's 128 columns of the row: sums of (x - pivot) and (x - pivot)^2 (see gemm2_sm100.cu, EPI_STATS)
+    float2 st_sum2 = make_float2(0.f, 0.f), st_sq2 = make_float2(0.f, 0.f), st_npiv2 = make_float2(0.f, 0.f);
     load_posb(pb_cur, col_base);
     mbar_wait(acc_bar, 0);
     tc_fence_after();
@@ -327,9 +328,11 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const Patc
                                        make_float2(pb_cur[i].z, pb_cur[i].w));
           v[4 * i + 0] = lo.x; v[4 * i + 1] = lo.y;
           v[4 * i + 2] = hi.x; v[4 * i + 3] = hi.y;
-          st_sum2 = __fadd2_rn(st_sum2, __fadd2_rn(lo, hi));
-          st_sq2 = __ffma2_rn(lo, lo, st_sq2);
-          st_sq2 = __ffma2_rn(hi, hi, st_sq2);
+          if (cc == 0 && i == 0) st_npiv2 = make_float2(-lo.x, -lo.x);   // pivot: the row's first value in the group
+          const float2 dlo = __fadd2_rn(lo, st_npiv2), dhi = __fadd2_rn(hi, st_npiv2);
+          st_sum2 = __fadd2_rn(st_sum2, __fadd2_rn(dlo, dhi));
+          st_sq2 = __ffma2_rn(dlo, dlo, st_sq2);
+          st_sq2 = __ffma2_rn(dhi, dhi, st_sq2);
         }
         const bool full_chunk = col + kStep <= p.D;
         if (p.out_f32) {
@@ -364,7 +367,8 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const Patc
 
     if (p.stats != nullptr && e_valid && col_base < p.D) {   // D % 128 == 0 (host): the group is all in or all out
       float2* dst = reinterpret_cast<float2*>(p.stats) + out_row * (p.D >> 7) + (col_base >> 7);
-      *dst = make_float2(st_sum2.x + st_sum2.y, st_sq2.x + st_sq2.y);
+      const float s_sh = st_sum2.x + st_sum2.y, q_sh = st_sq2.x + st_sq2.y;
+      *dst = make_float2(fmaf(-128.0f, st_npiv2.x, s_sh), fmaxf(fmaf(-s_sh * (1.0f / 128.0f), s_sh, q_sh), 0.f));
     }
 
     // CLS rows: the first row-tile of every column block writes cls + pos[0] for all images.
@@ -376,14 +380,15 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_w, const Patc
         const int gidx = idx - b * groups;
         const float* src = p.posb + n_blk * PE_BN + gidx * 128;
         float sx = 0.f, sq = 0.f;
+        const float piv = __ldg(src);
         for (int c = 0; c < 128; ++c) {
-          const float val = __ldg(src + c);
-          sx += val;
-          sq = fmaf(val, val, sq);
+          const float d = __ldg(src + c) - piv;
+          sx += d;
+          sq = fmaf(d, d, sq);
         }
         float2* dst = reinterpret_cast<float2*>(p.stats) + static_cast<long long>(b) * n_tok * (p.D >> 7) +
                       ((n_blk * PE_BN) >> 7) + gidx;
-        *dst = make_float2(sx, sq);
+        *dst = make_float2(fmaf(128.0f, piv, sx), fmaxf(fmaf(-sx * (1.0f / 128.0f), sx, sq), 0.f));
       }
     }
     if (m_blk == 0) {

@@ -85,62 +85,39 @@ def pack_mlp(block) -> SimpleNamespace:
     )
 
 
-def _fold_layernorm(w_nk: torch.Tensor, bias32: torch.Tensor, ln) -> tuple:
-    """Fold y = LN(x) into the dense layer that consumes it:  LN(x) @ W^T + b
-         = rstd * (x @ (W * gamma)^T) - rstd * mean * colsum(W * gamma) + (b + W @ beta).
-    Returns (W * gamma in the weight dtype, b + W @ beta in fp32, row sums of the ROUNDED folded weight)."""
-    w32 = w_nk.float()
-    w_fold = (w32 * ln.weight.detach().float()[None, :]).to(w_nk.dtype).contiguous()
-    b_fold = (bias32 + w32 @ ln.bias.detach().float()).contiguous()
-    colsum = w_fold.float().sum(dim=1).contiguous()
-    return w_fold, b_fold, colsum
+def fold_layernorm(w_nk: torch.Tensor, bias32: torch.Tensor, ln, zero_sum: bool = True) -> tuple:
+    """Fold y = LN(x) into the dense layer that consumes it (one launch of ``vt_ln_fold``, csrc/ln_fold.cu):
 
+        LN(x) @ W^T + b = rstd * (x @ (W * gamma)^T) - rstd * mean * colsum(W * gamma) + (b + W @ beta).
 
-def _fold_layernorm_zero_sum(w_nk: torch.Tensor, bias32: torch.Tensor, ln, passes: int = 6) -> tuple:
-    """The same fold with the mean term moved INTO the weights: every row of W * gamma is shifted by
-    its own mean, so that  x @ W'^T = x @ (W * gamma)^T - mean(x) * colsum(W * gamma)  comes out of the
-    GEMM itself and the epilogue is just  rstd * acc + (b + W @ beta)  — no column-sum operand, one FMA
-    per element less.  What is left of the mean term is  rstd * mean * sum_k(rounded W'[n, k]); the
-    rounding residue of each row (~3e-3 after plain bf16 rounding of a 768-wide row) is cancelled by
-    rounding a few elements the OTHER way — those closest to a rounding tie first, so the move costs
-    almost nothing in accuracy — which leaves |sum_k W'| at the 1e-6 level.  Returns (W', b + W @ beta)."""
-    w32 = w_nk.float()
-    wg = w32 * ln.weight.detach().float()[None, :]
-    b_fold = (bias32 + w32 @ ln.bias.detach().float()).contiguous()
-    exact = wg - wg.mean(dim=1, keepdim=True)
-    wz = exact.to(w_nk.dtype)
-    if w_nk.dtype == torch.bfloat16:
-        moved = torch.zeros(wz.shape, dtype=torch.bool, device=wz.device)   # every element moves at most once
-        for _ in range(passes):
-            f = wz.float()
-            resid = f.double().sum(dim=1).float()[:, None]                   # (N, 1): what has to go
-            # one bf16 ulp of every element: 2^(exponent - 7), built from the exponent field (integer ops only)
-            expo = (f.view(torch.int32) >> 23) & 0xFF
-            ulp = ((expo - 7).clamp_min(1) << 23).view(torch.float32)
-            err = exact - f                                                  # rounding error so far
-            ok = ~moved & (ulp <= resid.abs())
-            # added squared error per unit of residue removed: small for elements that were rounded
-            # the wrong way by almost half an ulp, large for those rounded the right way already
-            helps = err * resid < 0
-            price = torch.where(ok, ulp + torch.where(helps, -2.0, 2.0) * err.abs(), torch.full_like(ulp, float("inf")))
-            order = price.argsort(dim=1)
-            step = torch.where(ok, ulp, torch.zeros_like(ulp)).gather(1, order)
-            take = (step.cumsum(dim=1) <= resid.abs()) & (step > 0)          # cheapest prefix that fits
-            delta = torch.zeros_like(f).scatter(1, order, torch.where(take, step, torch.zeros_like(step)))
-            f = f - torch.sign(resid) * delta                                # exact: one ulp of each element
-            moved |= delta > 0
-            wz = f.to(torch.bfloat16)
-    return wz.contiguous(), b_fold
+    ``zero_sum`` (the default packing) moves the mean term INTO the weights: every row of W * gamma is
+    shifted by its own mean, so  x @ W'^T = x @ (W * gamma)^T - mean(x) * colsum  comes out of the GEMM
+    itself and the epilogue is  rstd * acc + (b + W @ beta)  — no column-sum operand, one FMA per element
+    less; the bf16 rounding residue of each row sum (~3e-3 for a 768-wide row) is cancelled in the kernel
+    by re-rounding the elements closest to a rounding tie the other way (left: ~1e-6).
+    Returns (W' bf16 [N, K], b' fp32 [N], colsum fp32 [N] or None for the zero-sum form)."""
+    assert w_nk.is_cuda and w_nk.dtype == torch.bfloat16 and w_nk.is_contiguous(), \
+        "LayerNorm folding runs on CUDA bf16 K-major weights (there is no CPU path)"
+    N, K = w_nk.shape
+    gamma = ln.weight.detach().float().contiguous()
+    beta = ln.bias.detach().float().contiguous()
+    bias32 = bias32.contiguous()
+    w_out = torch.empty_like(w_nk)
+    b_out = torch.empty((N,), device=w_nk.device, dtype=torch.float32)
+    colsum = None if zero_sum else torch.empty((N,), device=w_nk.device, dtype=torch.float32)
+    _lib.call("vt_ln_fold", w_nk.data_ptr(), K, bias32.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+              w_out.data_ptr(), K, b_out.data_ptr(), _lib.ptr(colsum), N, K, 1 if zero_sum else 0,
+              _lib.stream_ptr(w_nk))
+    return w_out, b_out, colsum
 
 
 def pack_block_folded(block) -> SimpleNamespace:
-    """layernorm_before folded into the QKV weights of one encoder block.  (layernorm_after -> fc1 is
-    NOT folded: the extra per-element FMAs land in the GELU epilogue, which already paces that GEMM —
-    measured +35 us per layer against the 31 us LayerNorm kernel it would remove.)"""
+    """Both LayerNorms of one encoder block folded into the GEMMs that consume them, zero-sum form:
+    layernorm_before -> fused QKV weights, layernorm_after -> fc1 weights (two ``vt_ln_fold`` launches)."""
     att = block.attention.packed()
     mlp = block.packed()
-    wqkv, bqkv = _fold_layernorm_zero_sum(att.wqkv, att.bqkv, block.layernorm_before)
-    w1, b1 = _fold_layernorm_zero_sum(mlp.w1, mlp.b1, block.layernorm_after)
+    wqkv, bqkv, _ = fold_layernorm(att.wqkv, att.bqkv, block.layernorm_before)
+    w1, b1, _ = fold_layernorm(mlp.w1, mlp.b1, block.layernorm_after)
     return SimpleNamespace(wqkv=wqkv, bqkv=bqkv, cqkv=None, w1=w1, b1=b1, c1=None)
 
 
@@ -223,7 +200,7 @@ def patch_embed_u8(emb, x: torch.Tensor, image_mean, image_std, rescale_factor: 
     return out
 
 
-STATS_COLS = 128   # columns per (sum, sumsq) partial of the row statistics (VT_LN_STATS_COLS in include/vitb200.h)
+STATS_COLS = 128   # columns per (sum, M2) partial of the row statistics (VT_LN_STATS_COLS in include/vitb200.h)
 
 
 def folding_supported(x: torch.Tensor, dim: int, mlp_dim: int) -> bool:
@@ -235,7 +212,7 @@ def linear_ln(x: torch.Tensor, w_fold: torch.Tensor, b_fold: torch.Tensor, colsu
               rowstats: torch.Tensor, eps: float, gelu: bool = False) -> torch.Tensor:
     """out = act(LN(x) @ W^T + b) computed as a GEMM on the un-normalised x with the normalisation
     applied per row in the epilogue; ``rowstats`` is the (M, K/128, 2) fp32 table of per-128-column
-    (sum, sumsq) partials of x's rows written by ``linear_res_stats``."""
+    (sum, M2) partials of x's rows written by ``linear_res_stats``."""
     B, N, K = x.shape
     n_out = w_fold.shape[0]
     out = torch.empty((B, N, n_out), device=x.device, dtype=x.dtype)
@@ -247,7 +224,7 @@ def linear_ln(x: torch.Tensor, w_fold: torch.Tensor, b_fold: torch.Tensor, colsu
 
 def linear_res_stats(x: torch.Tensor, w_nk: torch.Tensor, bias32: torch.Tensor, residual: torch.Tensor,
                      stats_out: torch.Tensor) -> torch.Tensor:
-    """out = x @ W^T + b + residual, also writing every output row's per-128-column (sum, sumsq) partials
+    """out = x @ W^T + b + residual, also writing every output row's per-128-column (sum, M2) partials
     into the (M, N/128, 2) fp32 ``stats_out`` for the LayerNorm folded into the next GEMM."""
     B, N, K = x.shape
     n_out = w_nk.shape[0]

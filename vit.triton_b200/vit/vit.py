@@ -39,7 +39,7 @@ from .kernels.layernorm import layernorm
 
 _FUSED = True
 # Both LayerNorms of a block are folded into the GEMM that consumes them: the normalisation is applied
-# per row in that GEMM's epilogue (zero-sum folded weights, packing._fold_layernorm_zero_sum) and the row
+# per row in that GEMM's epilogue (zero-sum folded weights, packing.fold_layernorm / csrc/ln_fold.cu) and the row
 # statistics come out of the epilogue of the GEMM that PRODUCES the row (fc2 of the previous block /
 # the patch embedding for layernorm_before, the out-proj for layernorm_after).  Measured in one process
 # under the sustained power cap (tools/fold_ab.py): 9.19 / 9.01 / 8.76 ms per forward with no fold / only
@@ -178,7 +178,7 @@ class Transformer(packing.PackedMixin, nn.Module):
     def forward_folded(self, x: torch.Tensor, ln1_stats: Optional[torch.Tensor]):
         """Block forward with layernorm_before folded into the QKV GEMM (bf16 only).
 
-        ``ln1_stats``: (M, D/128, 2) fp32 per-128-column (sum, sumsq) partials of x's rows, written by the
+        ``ln1_stats``: (M, D/128, 2) fp32 per-128-column (sum, M2) partials of x's rows, written by the
         previous block's last GEMM (None for the first block: layernorm_before then runs as a
         kernel).  Returns (output, statistics of the output rows).  5 launches per block (layernorm_after folded into
         fc1 as well, the default) instead of 7."""
