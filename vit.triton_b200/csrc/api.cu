@@ -20,20 +20,9 @@ int gemm2_bf16_tcgen05(const void*, long long, const void*, long long, void*, lo
                        const void*, long long, int, int, int, int, const float*, const float*, int, float,
                        float*, int, cudaStream_t);
 void gemm2_set_debug_buffer(void*);
-void attn2_set_debug_buffer(void*);
-void attn3_set_debug_buffer(void*);
-void attn4_set_debug_buffer(void*);
 void attn5_set_debug_buffer(void*);
 int simt_gemm(const void*, const void*, void*, const void*, int, int, int, int, int,
               const long long*, const long long*, const long long*, float, int, int, cudaStream_t);
-int attn_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
-                     long long, long long, long long, float, cudaStream_t);
-int attn2_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
-                      long long, long long, long long, float, int, cudaStream_t);
-int attn3_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
-                      long long, long long, long long, float, int, cudaStream_t);
-int attn4_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
-                      long long, long long, long long, float, int, cudaStream_t);
 int attn5_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
                       long long, long long, long long, float, int, cudaStream_t);
 int attn5mb_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
@@ -74,9 +63,6 @@ int vt_version(void) { return 100; }
 // Developer hook (not part of the public header): per-CTA cycle counters of the 2-CTA GEMM.
 void vt_debug_set_buffer(void* ptr) { vt::gemm2_set_debug_buffer(ptr); }
 void vt_debug_set_attn_buffer(void* ptr) {
-  vt::attn2_set_debug_buffer(ptr);
-  vt::attn3_set_debug_buffer(ptr);
-  vt::attn4_set_debug_buffer(ptr);
   vt::attn5_set_debug_buffer(ptr);
 }
 
@@ -148,34 +134,16 @@ int vt_gemm_strided(const void* A, const void* B, void* C, const void* bias, int
 int vt_flash_attn(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H,
                   int32_t N, int32_t dh, int64_t qkv_row_stride, int64_t qkv_batch_stride,
                   int64_t out_row_stride, int64_t out_batch_stride, float scale, void* stream) {
-  // Persistent kernels.  attn5 (two de-phased softmax groups over double-buffered scores) is the
-  // default: the single-block kernel for head dim 64 and N <= 208, the online-softmax multi-block
-  // kernel for longer sequences and for head dim 80 (ViT-H).  attn4 (one group of 16 warps) with
-  // VT_ATTN_IMPL=4 (N <= 208, or any N with VT_ATTN4_MULTIBLOCK=1); attn3 (two slots x two column
-  // halves, both head dims) with VT_ATTN_IMPL=3.  VT_ATTN_IMPL=3 / 2 / 1 force attn3 / attn2 /
-  // the one-tile-per-CTA kernel.  The alternatives exist for A/B measurements.
-  // (read on every call — a getenv is nothing next to a launch — so tests can exercise every variant)
-  const char* e = getenv("VT_ATTN_IMPL");
-  const int impl = (e && e[0] >= '1' && e[0] <= '4') ? (e[0] - '0') : 5;
-  if (impl == 5 && dh == 64 && N <= 208)
+  // Persistent two-group kernels (csrc/attn5_sm100.cu): the single-block kernel for head dim 64 and
+  // N <= 208, the online-softmax multi-block kernel for longer sequences and for head dim 80 (ViT-H).
+  // Anything else returns VT_ERR_UNSUPPORTED and the host shim takes the exact strided path.
+  if (dh == 64 && N <= 208)
     return vt::attn5_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
                                  out_row_stride, out_batch_stride, scale, next_direction(), S(stream));
-  if (impl == 5 && (dh == 64 || dh == 80)) {   // N > 208 and / or head dim 80: per-group unit streams
-    const int rc = vt::attn5mb_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
-                                           out_row_stride, out_batch_stride, scale, next_direction(), S(stream));
-    if (rc != VT_ERR_UNSUPPORTED) return rc;
-  }
-  if (impl >= 4 && dh == 64 && (N <= 208 || getenv("VT_ATTN4_MULTIBLOCK")))
-    return vt::attn4_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
-                                 out_row_stride, out_batch_stride, scale, next_direction(), S(stream));
-  if (impl >= 3)
-    return vt::attn3_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
-                                 out_row_stride, out_batch_stride, scale, next_direction(), S(stream));
-  if (impl == 2)
-    return vt::attn2_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
-                                 out_row_stride, out_batch_stride, scale, next_direction(), S(stream));
-  return vt::attn_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
-                              out_row_stride, out_batch_stride, scale, S(stream));
+  if (dh == 64 || dh == 80)
+    return vt::attn5mb_fwd_tcgen05(q, k, v, out, B, H, N, dh, qkv_row_stride, qkv_batch_stride,
+                                   out_row_stride, out_batch_stride, scale, next_direction(), S(stream));
+  return VT_ERR_UNSUPPORTED;
 }
 
 int vt_patch_embed(const void* pixels, int32_t pix_dtype, const void* w, int64_t ldw,

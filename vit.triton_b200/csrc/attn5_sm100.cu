@@ -25,7 +25,7 @@
 //   warp 17           MMA issuer: per item v: wait P_v, V_v, O_{v-1} read | PV_v (+ row sums) |
 //                     S_{v+2} = Q K^T into S[v & 1]
 //
-// Sequences longer than 208 keys and head dim 80 stay on attn3_sm100.cu.
+// Sequences longer than 208 keys and head dim 80 run attn5mb_fwd_kernel below (online softmax over KV blocks).
 #include "attn_softmax.cuh"
 #include "common.cuh"
 #include "tensormap.h"

@@ -1,4 +1,4 @@
-// Softmax building blocks shared by the persistent attention kernels (attn3_sm100.cu, attn4_sm100.cu):
+// Softmax building blocks shared by the persistent attention kernels (attn5_sm100.cu; the superseded generations under tools/attn_generations/):
 // row max and exp2 / bf16-P passes of one thread over a range of its row's score columns in TMEM.
 #pragma once
 

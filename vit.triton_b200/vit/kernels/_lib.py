@@ -83,14 +83,19 @@ def load() -> ctypes.CDLL:
     return lib
 
 
+VT_ERR_UNSUPPORTED = -4
+
+
 class KernelError(RuntimeError):
-    pass
+    def __init__(self, message: str, status: int = 0):
+        super().__init__(message)
+        self.status = status
 
 
 def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load().vt_status_string(rc).decode()
-        raise KernelError(f"{what} failed: {msg} (status {rc})")
+        raise KernelError(f"{what} failed: {msg} (status {rc})", rc)
 
 
 def dtype_code(t: torch.Tensor) -> int:

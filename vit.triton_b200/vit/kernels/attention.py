@@ -33,13 +33,19 @@ def flash_attention(qkv: torch.Tensor, num_heads: int, scale: Optional[float] = 
 
     if qkv.dtype == torch.bfloat16 and dh in (64, 80) and qkv.stride(1) % 8 == 0 and qkv.stride(0) % 8 == 0 \
             and base % 16 == 0:
-        for b0 in range(0, B, 32768):
-            nb = min(32768, B - b0)
-            off = b0 * qkv.stride(0) * es
-            _lib.call("vt_flash_attn", base + off, base + off + D * es, base + off + 2 * D * es,
-                      out[b0:].data_ptr(), nb, num_heads, N, dh, qkv.stride(1), qkv.stride(0), D, N * D,
-                      float(scale), stream)
-        return out
+        try:
+            for b0 in range(0, B, 32768):
+                nb = min(32768, B - b0)
+                off = b0 * qkv.stride(0) * es
+                _lib.call("vt_flash_attn", base + off, base + off + D * es, base + off + 2 * D * es,
+                          out[b0:].data_ptr(), nb, num_heads, N, dh, qkv.stride(1), qkv.stride(0), D, N * D,
+                          float(scale), stream)
+            return out
+        except _lib.KernelError as exc:
+            # a shape outside what the tensor-core kernels implement (e.g. a sequence whose K/V block does
+            # not fit shared memory) is refused before anything is launched: the strided path below is exact
+            if exc.status != _lib.VT_ERR_UNSUPPORTED:
+                raise
 
     # exact / odd-head-dim path: scores, softmax and PV as three strided launches over (B, H)
     scores = torch.empty((B * num_heads, N, N), device=qkv.device, dtype=qkv.dtype)

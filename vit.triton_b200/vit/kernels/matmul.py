@@ -11,23 +11,32 @@ import torch
 
 from . import _lib
 
-# id(tensor) -> (weakref, version, derived tensor).  Only nn.Parameters are cached: a plain tensor's
-# storage can be recycled by the allocator under the same pointer, a live Parameter's cannot.
+# (id(tensor), tag) -> (weakref, (data_ptr, version), derived tensor).  Only nn.Parameters are cached: a plain
+# tensor's storage can be recycled by the allocator under the same pointer, a live Parameter's cannot.
+# The key covers in-place updates through the autograd-visible API (version counter) and re-pointing
+# (``p.data = other``: data_ptr); writes THROUGH ``p.data`` (``p.data.copy_()``, ``p.data.normal_()``, EMA
+# updates) change neither — call ``VIT.invalidate_packed()`` / ``clear_derived_cache()`` after those.
 _derived_cache = {}
+
+
+def clear_derived_cache() -> None:
+    """Drop every cached K-major / fp32 copy of a parameter (see the note above)."""
+    _derived_cache.clear()
 
 
 def _cached(param: torch.Tensor, tag: str, make):
     key = (id(param), tag)
+    stamp = (param.data_ptr(), param._version)
     hit = _derived_cache.get(key)
     if hit is not None:
-        ref, version, value = hit
-        if ref() is param and version == param._version and value.device == param.device:
+        ref, old_stamp, value = hit
+        if ref() is param and old_stamp == stamp and value.device == param.device:
             return value
     value = make(param)
     if isinstance(param, torch.nn.Parameter):
         if len(_derived_cache) > 4096:
             _derived_cache.clear()
-        _derived_cache[key] = (weakref.ref(param), param._version, value)
+        _derived_cache[key] = (weakref.ref(param), stamp, value)
     return value
 
 

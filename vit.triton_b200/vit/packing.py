@@ -6,7 +6,10 @@ kernels want something else: ONE K-major [3D, D] matrix for Q, K and V of all he
 [out, in] matrices for the other dense layers, fp32 biases, and the position embedding pre-added to
 the CLS token / conv bias.  This module derives those once and caches them per module; the cache is
 dropped when the module is moved / cast (``_apply``), when a state-dict is loaded, or when any
-source parameter's storage pointer or version counter changes.
+source parameter's storage pointer or version counter changes (in-place ops, optimizer steps,
+``p.data = new``).  Writes THROUGH ``p.data`` (``p.data.copy_()``, ``p.data.normal_()``, EMA updates)
+bump no version counter and cannot be seen without reading the device: call ``VIT.invalidate_packed()``
+after them.
 """
 from types import SimpleNamespace
 from typing import Optional

@@ -349,6 +349,19 @@ class VIT(nn.Module):
         # state-dict keys classifier.{weight,bias}
         self.classifier = LinearWithBias(self.hidden_dim, num_labels) if num_labels else None
 
+    def invalidate_packed(self) -> None:
+        """Drop every derived weight (packed / LayerNorm-folded / uint8-scaled operands of all sub-modules
+        and the K-major copies the ``matmul`` entry point keeps).  Needed only after writes that go THROUGH
+        ``param.data`` (``p.data.copy_()``, HF-style re-initialisation, EMA): those change neither the
+        storage pointer nor the version counter the caches are keyed on; every other kind of update is
+        noticed automatically."""
+        from .kernels.matmul import clear_derived_cache
+        for m in self.modules():
+            if isinstance(m, packing.PackedMixin):
+                m.invalidate_packed()
+            m.__dict__.pop("_u8_pack", None)
+        clear_derived_cache()
+
     @property
     def device(self) -> torch.device:
         return self.layernorm.weight.device
