@@ -4,16 +4,25 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c3|c4|c5] [--impl reference]
 
 One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1).  A step = one forward
-of the per-GPU batch (weak scaling: the per-GPU batch is fixed) + CLS pooling + the all-gather of
-the pooled embeddings when N > 1 (one pool + peer-store kernel over NVLink, vit/parallel.py:PeerGather;
-VT_PEER_GATHER=0 = vt_pool_cls + NCCL; `config.gather` says which ran).  Rank 0 prints ONE JSON line.
+of the per-GPU batch (c2 / c3: weak scaling, the per-GPU batch is fixed; c4 / c5: the named GLOBAL batch
+divided by N) + CLS pooling + the all-gather of the pooled embeddings when N > 1 (one pool +
+peer-store kernel over NVLink, vit/parallel.py:PeerGather, pipelined: step i hands its rows to the
+peers and collects step i - 1, the last step is drained inside the timed region; VT_PEER_GATHER=0 =
+vt_pool_cls + NCCL; `config.gather` says which ran).  The step is replayed from a CUDA graph (the
+reference's own contract, vit/utils.py:115-133; `config.launch` says so, --no-graph = eager).
+Rank 0 prints ONE JSON line.
 
   value     device-resident inputs, CUDA-event timed, max over ranks
   e2e       same steps through the public API from PINNED HOST buffers: H2D of every step's pixels
             and D2H of its pooled embeddings inside the timed region (double-buffered copy stream)
   roofline  the tcgen05 GEMM kernel (95 % of the FLOPs): algorithmic FLOPs / CUDA-event time of its
-            launches, against MEASURED_PEAKS.json; the events are recorded in a SECOND pass over the
-            same K steps so that the timed region of `value` holds nothing but the steps
+            launches, against MEASURED_PEAKS.json (burst figure for a timed region under 1 s, sustained
+            above; both fractions are printed); `roofline.kernels` = the same for every kernel of the
+            step (attention against the tensor AND the exp/MUFU bound, patch embedding and LayerNorm in
+            GB/s).  The events are recorded in a SECOND, eager pass over the same K steps so that the
+            timed region of `value` holds nothing but the steps
+  gather_check (N > 1)  one untimed step: peer-store gather == NCCL gather == single-process forward
+  other_configs         short untimed-side measurements of the other BASELINE configs on the same box
   cpu_baseline / --impl reference
             HuggingFace ViTModel fp32 on the box's host cores (the oracle and timing reference
             BASELINE.json names; the reference's own Triton kernels cannot run on a CPU).
@@ -33,12 +42,22 @@ for _p in (ROOT, os.path.join(ROOT, "vit.triton_b200")):
         sys.path.insert(0, _p)
 
 CONFIGS = {
-    # name: (arch, per-GPU batch, description)
-    "c2": ("vit-b16-224", 256, "ViT-B/16@224 bf16 forward, batch 256 per GPU (BASELINE configs[1])"),
-    "c3": ("vit-b16-384", 128, "ViT-B/16@384 (577 tokens) bf16 forward, batch 128 per GPU (BASELINE configs[2])"),
-    "c4": ("vit-l16-224", 128, "ViT-L/16@224 bf16 forward, batch 128 per GPU (BASELINE configs[3] at 8 GPUs)"),
-    "c5": ("vit-h14-224", 256, "ViT-H/14@224 bf16 forward, batch 256 per GPU (BASELINE configs[4])"),
+    # name: (arch, batch, "per_gpu" | "global", description).  c2 / c3 are quoted per GPU (weak scaling: the
+    # metric's config is 256 images on ONE B200); c4 / c5 name a GLOBAL batch sharded over the GPUs
+    # (1024 / N and 2048 / N images per GPU).
+    "c2": ("vit-b16-224", 256, "per_gpu", "ViT-B/16@224 bf16 forward, batch 256 per GPU (BASELINE configs[1])"),
+    "c3": ("vit-b16-384", 128, "per_gpu", "ViT-B/16@384 (577 tokens) bf16 forward, batch 128 per GPU (BASELINE configs[2])"),
+    "c4": ("vit-l16-224", 1024, "global", "ViT-L/16@224 bf16 forward, global batch 1024 sharded over the GPUs (BASELINE configs[3])"),
+    "c5": ("vit-h14-224", 2048, "global", "ViT-H/14@224 bf16 forward, global batch 2048 sharded over the GPUs (BASELINE configs[4])"),
 }
+
+
+def per_gpu_batch(config: str, world: int) -> int:
+    _, batch, kind, _ = CONFIGS[config]
+    if kind == "global":
+        assert batch % world == 0, f"{config}: global batch {batch} does not divide over {world} GPUs"
+        return batch // world
+    return batch
 
 
 def flops_per_image(a):
@@ -180,47 +199,11 @@ def run_reference(args, arch, desc):
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
-    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--profile-step", action="store_true",
-                    help="bracket ONE extra step after the timed region with cudaProfilerStart/Stop "
-                         "(ncu --profile-from-start off then captures exactly one forward)")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
-
-    arch, batch, desc = CONFIGS[args.config]
-    if args.batch:
-        batch = args.batch
-    if args.impl == "reference":
-        run_reference(args, arch, desc)
-        return
-
+def build_model(arch, dev, dtype):
+    """Random-init weights of the named architecture (no network for checkpoints), same on all ranks."""
     import torch
-    import torch.distributed as dist
     from vit import configs
-    from vit.kernels import _lib
-    from vit.parallel import DataParallelVIT
     from vit.vit import VIT
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.load()
-
-    a = configs.ARCHS[arch]
-    # random-init weights of the named architecture (no network for checkpoints), same on all ranks
     torch.manual_seed(0)
     model = VIT(**configs.vit_kwargs(arch))
     with torch.no_grad():
@@ -232,7 +215,268 @@ def main():
         for m in model.modules():
             if type(m).__name__ == "LayerNormTriton":
                 m.weight.add_(1.0)
-    model = model.to(device=dev, dtype=torch.bfloat16).eval()
+    return model.to(device=dev, dtype=dtype).eval()
+
+
+def classify_launch(name, args):
+    """(label, flops, bytes) of one C-ABI call from its argument tuple (include/vitb200.h order)."""
+    if name == "vt_gemm_bf16":
+        M, N, K, gelu, res = args[10], args[11], args[12], args[13], args[8]
+        return f"gemm N={N} K={K}" + ("+gelu" if gelu else "") + ("+res" if res else ""), 2.0 * M * N * K, None
+    if name == "vt_gemm_bf16_ln":
+        M, N, K, gelu, res, rs, so = args[9], args[10], args[11], args[12], args[7], args[13], args[17]
+        tag = ("+ln" if rs else "") + ("+gelu" if gelu else "") + ("+res" if res else "") + ("+stats" if so else "")
+        return f"gemm N={N} K={K}{tag}", 2.0 * M * N * K, None
+    if name == "vt_flash_attn":
+        B, H, N, dh = args[4], args[5], args[6], args[7]
+        return f"attention N={N} dh={dh}", 4.0 * B * H * N * N * dh, None
+    if name in ("vt_patch_embed", "vt_patch_embed_stats"):
+        o = 1 if name == "vt_patch_embed_stats" else 0
+        pix_dtype, B, C, S, P, D = args[1], args[7 + o], args[8 + o], args[9 + o], args[10 + o], args[11 + o]
+        es = {0: 4, 1: 2, 2: 1}[pix_dtype]
+        n = (S // P) ** 2
+        return "patch_embed", 2.0 * B * n * C * P * P * D, float(B) * (C * S * S * es + (n + 1) * D * 2) + C * P * P * D * 2
+    if name == "vt_layernorm":
+        rows, dim, in_dt, out_dt = args[4], args[5], args[9], args[10]
+        return "layernorm", None, float(rows) * dim * ({0: 4, 1: 2}[in_dt] + {0: 4, 1: 2}[out_dt])
+    if name == "vt_pool_cls":
+        return "pool_cls", None, 2.0 * args[2] * args[3] * 2
+    if name == "vt_pool_cls_allgather":
+        return "pool_cls_allgather", None, None
+    return name, None, None
+
+
+class KernelTimer:
+    """CUDA events around every launch issued through vit.kernels._lib.call (eager passes only)."""
+
+    def __init__(self):
+        self.records = []      # (label, flops, bytes, ev0, ev1)
+        self._open = None
+
+    def hook(self, name, before, args):
+        import torch
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        if before:
+            self._open = (classify_launch(name, args), ev)
+        else:
+            (label, flops, nbytes), ev0 = self._open
+            self.records.append((label, flops, nbytes, ev0, ev))
+
+    def summary(self):
+        agg = {}
+        for label, flops, nbytes, ev0, ev1 in self.records:
+            a = agg.setdefault(label, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            a["launches"] += 1
+            a["ms"] += ev0.elapsed_time(ev1)
+            a["flops"] += flops or 0.0
+            a["bytes"] += nbytes or 0.0
+        return agg
+
+
+def roofline_kernels(agg, peaks, tensor_peak, sm_mhz, steps):
+    """Per-kernel roofline entries from a KernelTimer summary."""
+    out = []
+    for label, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        sec = a["ms"] / 1e3
+        e = {"kernel": label, "launches_per_step": a["launches"] / steps, "avg_launch_us": a["ms"] * 1e3 / a["launches"],
+             "ms_per_step": a["ms"] / steps}
+        if label.startswith("gemm"):
+            tf = a["flops"] / sec / 1e12
+            e.update(bound="tensor", achieved=tf, peak=tensor_peak, unit="TFLOP/s", frac=tf / tensor_peak)
+        elif label.startswith("attention"):
+            tf = a["flops"] / sec / 1e12
+            # one exponential per score: flops / (4 dh); the MUFU pipe issues 16 per clock and SM
+            dh = int(label.split("dh=")[1])
+            exps = a["flops"] / (4.0 * dh) / sec
+            mufu_peak = 16.0 * 148 * (sm_mhz or 1965.0) * 1e6
+            e.update(bound="tensor", achieved=tf, peak=tensor_peak, unit="TFLOP/s", frac=tf / tensor_peak,
+                     exp_per_s=exps, exp_peak_per_s=mufu_peak, frac_of_exp_bound=exps / mufu_peak,
+                     exp_peak_note="16 ex2 per clock per SM x 148 SMs at the SM clock sampled during the run")
+        elif label == "patch_embed":
+            gbs = a["bytes"] / sec / 1e9
+            e.update(bound="hbm", achieved=gbs, peak=peaks["hbm"], unit="GB/s", frac=gbs / peaks["hbm"],
+                     tflops=a["flops"] / sec / 1e12)
+        elif a["bytes"]:
+            gbs = a["bytes"] / sec / 1e9
+            e.update(bound="hbm", achieved=gbs, peak=peaks["hbm"], unit="GB/s", frac=gbs / peaks["hbm"])
+        out.append(e)
+    return out
+
+
+class StepRunner:
+    """One step of the data-parallel forward, replayed from a CUDA graph per input buffer when possible."""
+
+    def __init__(self, dp, world, global_batch, use_graph):
+        self.dp, self.world, self.global_batch = dp, world, global_batch
+        self.use_graph = use_graph
+        self.graphs = {}
+        self.launches_per_graph = 0
+        self.note = "eager launches"
+
+    def eager(self, x):
+        if self.world > 1:
+            return self.dp.submit(x, self.global_batch)
+        return self.dp(x)
+
+    def finish(self):
+        """Collect the last step's gathered rows (pipelined gather); None on one GPU."""
+        return self.dp.flush() if self.world > 1 else None
+
+    def capture(self, buffers):
+        import torch
+        from vit.kernels import _lib
+        if not self.use_graph:
+            return
+        if self.world > 1 and self.dp.gather_impl != "peer-store kernel":
+            self.note = "eager launches (NCCL gather is not captured)"
+            return
+        try:
+            if self.world > 1 and not self.dp._pending:
+                self.eager(buffers[0])     # the captured step must contain the collect of its predecessor
+                torch.cuda.synchronize()
+            pool = torch.cuda.graph_pool_handle()   # the graphs run one after the other: one activation pool
+            for b in buffers:
+                n0 = _lib.launch_count
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    out = self.eager(b)
+                self.launches_per_graph = _lib.launch_count - n0
+                self.graphs[b.data_ptr()] = (g, out)
+            self.note = f"CUDA-graph replay ({self.launches_per_graph} kernel launches per graph)"
+        except Exception as exc:   # capture refused: fall back to eager launches and say so
+            self.graphs = {}
+            self.note = f"eager launches (graph capture failed: {type(exc).__name__})"
+            torch.cuda.synchronize()
+
+    def __call__(self, x):
+        hit = self.graphs.get(x.data_ptr())
+        if hit is None:
+            return self.eager(x)
+        hit[0].replay()
+        return hit[1]
+
+    def launches(self, steps, eager_count):
+        return self.launches_per_graph * steps if self.graphs else eager_count
+
+
+def quick_config(name, world, rank, dev, steps=5, warmup=3):
+    """Short device-resident measurement of another BASELINE config on the same box (side field)."""
+    import torch
+    from vit import configs
+    from vit.parallel import DataParallelVIT
+    arch = CONFIGS[name][0]
+    batch = per_gpu_batch(name, world)
+    a = configs.ARCHS[arch]
+    model = build_model(arch, dev, torch.bfloat16)
+    dp = DataParallelVIT(model)
+    S = a["image_size"]
+    g = torch.Generator().manual_seed(99 + rank)
+    xs = [torch.randn((batch, 3, S, S), generator=g).to(torch.bfloat16).to(dev) for _ in range(2)]
+    run = StepRunner(dp, world, batch * world, use_graph=False)
+    with torch.no_grad():
+        for i in range(warmup):
+            run(xs[i & 1])
+        run.finish()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            run(xs[i & 1])
+        run.finish()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del model, dp, xs
+    torch.cuda.empty_cache()
+    return {"arch": arch, "per_gpu_batch": batch, "global_batch": batch * world, "ms_per_step": ms, "steps": steps,
+            "flops_per_image": flops_per_image(a)}
+
+
+def c1_fp32_latency(dev, reps=20):
+    """BASELINE configs[0] on the GPU: ViT-B/16@224 fp32, batch 1 — a latency figure (ms per image)."""
+    import torch
+    model = build_model("vit-b16-224", dev, torch.float32)
+    x = torch.randn(1, 3, 224, 224, device=dev)
+    with torch.no_grad():
+        for _ in range(3):
+            model(x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            model(x)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    del model
+    torch.cuda.empty_cache()
+    return {"arch": "vit-b16-224", "dtype": "f32", "batch": 1, "ms_per_image": ms, "img_s": 1e3 / ms, "reps": reps}
+
+
+def gather_check(model, dp, x, global_batch, world, rank):
+    """One untimed step three ways: peer-store kernel, NCCL all-gather, and (rank 0) the single-process
+    forward of the first images of every rank's shard.  Returns a dict of verdicts (identical on all ranks)."""
+    import torch
+    import torch.distributed as dist
+    from vit.parallel import DataParallelVIT
+    with torch.no_grad():
+        a = dp(x, global_batch).clone()
+        via_nccl = DataParallelVIT(model, peer_gather=False)(x, global_batch)
+        k = min(8, x.shape[0])
+        heads = torch.empty((world * k,) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
+        dist.all_gather_into_tensor(heads, x[:k].contiguous())
+        whole = model.pooled(heads)
+        rows = torch.cat([a[r * x.shape[0]: r * x.shape[0] + k] for r in range(world)], dim=0)
+    ok = torch.tensor([int(torch.equal(a, via_nccl)), int(torch.equal(rows, whole))], device=x.device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    ok = ok.tolist()
+    return {"gather": dp.gather_impl, "vs_nccl_all_gather": "bit-equal" if ok[0] else "MISMATCH",
+            "vs_single_process_forward": ("bit-equal" if ok[1] else "MISMATCH") +
+            f" (first {k} images of every rank's shard recomputed in one process on each rank)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the side measurements of the other BASELINE configs")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="bracket ONE extra eager step after the timed region with cudaProfilerStart/Stop "
+                         "(ncu --profile-from-start off then captures exactly one forward)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    arch, _, _, desc = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, arch, desc)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from vit import configs
+    from vit.kernels import _lib
+    from vit.parallel import DataParallelVIT
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    batch = args.batch or per_gpu_batch(args.config, world)
+    a = configs.ARCHS[arch]
+    model = build_model(arch, dev, torch.bfloat16)
     dp = DataParallelVIT(model)
     global_batch = batch * world
 
@@ -244,47 +488,47 @@ def main():
     dev_inputs = [h.to(dev, non_blocking=True) for h in host_inputs]
     torch.cuda.synchronize()
 
-    def step(x):
-        return dp(x, global_batch)
-
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
 
+    run = StepRunner(dp, world, global_batch, use_graph=not args.no_graph)
+
     # ----------------------------------------------------------------- device-resident timing
-    gemm_events = []
-
-    def hook(name, before):
-        if name in ("vt_gemm_bf16", "vt_gemm_bf16_ln"):   # the same kernel with / without the LayerNorm fold
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            gemm_events.append(ev)
-
     with torch.no_grad():
+        check = gather_check(model, dp, dev_inputs[0], global_batch, world, rank) if world > 1 else None
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()          # nvidia-smi needs ~0.5 s to produce its first sample
         for i in range(args.warmup):
-            step(dev_inputs[i % n_rot])
+            run.eager(dev_inputs[i % n_rot])
         sync_all()
-        # timed region: EXACTLY K steps, nothing but the steps between the two events
+        run.capture(dev_inputs)
+        for i in range(args.warmup):   # warm-up in the form that is timed (graph replays)
+            run(dev_inputs[i % n_rot])
+        run.finish()
+        sync_all()
+        # timed region: EXACTLY K steps (+ the drain of the last step's gather), nothing else between the events
         launches0 = _lib.launch_count
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
         for i in range(args.steps):
-            out = step(dev_inputs[i % n_rot])
+            out = run(dev_inputs[i % n_rot])
+        last = run.finish()
         stop.record()
         sync_all()
-        launches = _lib.launch_count - launches0
-        # the same K steps again with a CUDA event before and after every GEMM launch (roofline of the
-        # dominant kernel); kept out of the region above because 96 event records per step cost 2-4 %
-        _lib.event_hook = hook
+        launches = run.launches(args.steps, _lib.launch_count - launches0)
+        # the same K steps again, eagerly, with a CUDA event before and after EVERY kernel launch (rooflines);
+        # kept out of the region above because ~130 event records per step cost 2-4 %
+        timer = KernelTimer()
+        _lib.event_hook = timer.hook
         h_start, h_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         h_start.record()
         for i in range(args.steps):
-            out = step(dev_inputs[i % n_rot])
+            out = run.eager(dev_inputs[i % n_rot])
+        run.finish()
         h_stop.record()
         _lib.event_hook = None
         sync_all()
@@ -293,22 +537,24 @@ def main():
         with torch.no_grad():
             torch.cuda.synchronize()
             torch.cuda.profiler.start()
-            step(dev_inputs[0])
+            run.eager(dev_inputs[0])
+            run.finish()
             torch.cuda.synchronize()
             torch.cuda.profiler.stop()
     ms_total = start.elapsed_time(stop)
     hooked_ms_total = h_start.elapsed_time(h_stop)
-    gemm_ms = sum(gemm_events[i].elapsed_time(gemm_events[i + 1]) for i in range(0, len(gemm_events), 2))
-    n_gemm = len(gemm_events) // 2
+    kagg = timer.summary()
+    gemm_ms = sum(v["ms"] for k, v in kagg.items() if k.startswith("gemm"))
+    n_gemm = sum(v["launches"] for k, v in kagg.items() if k.startswith("gemm"))
+    kernels_ms = sum(v["ms"] for v in kagg.values())
 
     # ----------------------------------------------------------------- end-to-end from pinned host memory
     copy_stream = torch.cuda.Stream()
-    bufs = [torch.empty_like(dev_inputs[0]) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     pooled_host = torch.empty((global_batch, a["hidden_size"]), dtype=torch.bfloat16).pin_memory()
 
-    def e2e_run(nsteps, hosts, devs):
+    def e2e_run(nsteps, hosts, devs, runner):
         cur = torch.cuda.current_stream()
         with torch.cuda.stream(copy_stream):
             devs[0].copy_(hosts[0], non_blocking=True)
@@ -323,24 +569,32 @@ def main():
                     devs[nxt].copy_(hosts[(i + 1) % n_rot], non_blocking=True)
                     ready[nxt].record(copy_stream)
             cur.wait_event(ready[slot])
-            res = step(devs[slot])
+            res = runner(devs[slot])
             consumed[slot].record(cur)
+            if res is not None:          # pipelined gather: the rows of the previous step (None at step 0)
+                pooled_host.copy_(res, non_blocking=True)
+        res = runner.finish()
+        if res is not None:
             pooled_host.copy_(res, non_blocking=True)
-        return res
 
     def e2e_time(hosts, devs):
+        runner = StepRunner(dp, world, global_batch, use_graph=not args.no_graph)
         with torch.no_grad():
-            e2e_run(3, hosts, devs)
+            e2e_run(3, hosts, devs, runner)
+            sync_all()
+            runner.capture(devs)
+            e2e_run(3, hosts, devs, runner)
             sync_all()
             e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t_host0 = time.perf_counter()
             e_start.record()
-            e2e_run(args.steps, hosts, devs)
+            e2e_run(args.steps, hosts, devs, runner)
             e_stop.record()
             sync_all()
             wall = (time.perf_counter() - t_host0) * 1e3
         return max(e_start.elapsed_time(e_stop), 0.0), wall
 
+    bufs = [torch.empty_like(dev_inputs[0]) for _ in range(2)]
     e2e_ms, e2e_wall_ms = e2e_time(host_inputs, bufs)
     # same steps from RAW uint8 NHWC host pixels: the image processor's rescale + normalise run inside
     # the patch-embedding kernel (VIT.forward_uint8), so the H2D copy is one byte per pixel value
@@ -350,8 +604,21 @@ def main():
     bufs_u8 = [torch.empty((batch, S, S, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
     e2e_u8_ms, _ = e2e_time(host_u8, bufs_u8)
 
+    # ----------------------------------------------------------------- other BASELINE configs, same box (side fields)
+    others = {}
+    if not args.no_other_configs and args.config == "c2" and not args.batch:
+        del bufs, bufs_u8
+        torch.cuda.empty_cache()
+        names = ["c3"] if world == 1 else ["c4"] + (["c5"] if world == 8 else [])
+        with torch.no_grad():
+            for name in names:
+                others[name] = quick_config(name, world, rank, dev)
+            if world == 1:
+                others["c1"] = c1_fp32_latency(dev)
+
     # ----------------------------------------------------------------- reduce over ranks
-    stats = torch.tensor([ms_total, e2e_ms, gemm_ms, float(launches), e2e_u8_ms], device=dev, dtype=torch.float64)
+    other_ms = [others[k]["ms_per_step"] for k in sorted(others) if "ms_per_step" in others[k]]
+    stats = torch.tensor([ms_total, e2e_ms, gemm_ms, float(launches), e2e_u8_ms] + other_ms, device=dev, dtype=torch.float64)
     if world > 1:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -359,6 +626,8 @@ def main():
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms_total, e2e_ms, e2e_u8_ms = mx[0].item(), mx[1].item(), mx[4].item()
         launches = int(sm[3].item())
+        for k, v in zip([k for k in sorted(others) if "ms_per_step" in others[k]], mx[5:].tolist()):
+            others[k]["ms_per_step"] = v
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -369,6 +638,11 @@ def main():
     e2e_value = global_batch * args.steps / (e2e_ms / 1e3)
     fpi = flops_per_image(a)
     peaks = measured_peaks()
+    # burst peak for a timed region shorter than about a second (the power cap has not bitten yet: the
+    # driver's own burst figure is a best-of-10 of ~1 ms GEMMs), the sustained one above
+    region_s = ms_total / 1e3
+    use_burst = region_s < 1.0
+    tensor_peak = peaks["burst"] if use_burst else peaks["sustained"]
 
     # GEMM FLOPs per step on this rank (QKV, proj, fc1, fc2 of every layer; patch-embed and attention
     # are separate kernels and not counted here)
@@ -383,37 +657,54 @@ def main():
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    whole_tf = fpi * batch / (ms_per_step / 1e3) / 1e12
     roofline = {
         "kernel": "gemm2_bf16_kernel (tcgen05 cta_group::2)", "bound": "tensor", "achieved": gemm_tflops,
-        "peak": peaks["sustained"], "unit": "TFLOP/s",
-        "frac": (gemm_tflops / peaks["sustained"]) if gemm_tflops else None,
+        "peak": tensor_peak, "unit": "TFLOP/s",
+        "frac": (gemm_tflops / tensor_peak) if gemm_tflops else None,
         "frac_of_burst_peak": (gemm_tflops / peaks["burst"]) if gemm_tflops else None,
-        "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+        "frac_of_sustained_peak": (gemm_tflops / peaks["sustained"]) if gemm_tflops else None,
+        "peak_source": peaks["source"] + (f", burst figure (timed region {region_s:.2f} s < 1 s)" if use_burst else
+                                          f", sustained figure (timed region {region_s:.2f} s under the power cap)"),
         "traffic": traffic, "launches_timed": n_gemm,
         "avg_launch_us": (gemm_ms / n_gemm * 1e3) if n_gemm else None,
         "algorithmic_flops_per_launch": gemm_flops_step / (4 * L),
         "share_of_step": gemm_ms / hooked_ms_total,
-        "timed_in": "a second pass over the same K steps with a CUDA event around every GEMM launch "
+        "timed_in": "a second, eager pass over the same K steps with a CUDA event around every kernel launch "
                     f"({hooked_ms_total / args.steps:.3f} ms per step with the events)",
-        "whole_forward_tflops": fpi * batch / (ms_per_step / 1e3) / 1e12,
-        "whole_forward_frac_of_burst_peak": fpi * batch / (ms_per_step / 1e3) / 1e12 / peaks["burst"],
+        "whole_forward_tflops": whole_tf,
+        "whole_forward_frac_of_burst_peak": whole_tf / peaks["burst"],
+        "whole_forward_frac_of_sustained_peak": whole_tf / peaks["sustained"],
+        "kernel_time_ms_per_step": kernels_ms / args.steps,
+        "launch_gap_ms_per_step": ms_per_step - kernels_ms / args.steps,
+        "kernels": roofline_kernels(kagg, peaks, tensor_peak, (clocks or {}).get("sm_mhz"), args.steps),
     }
+    for k, o in others.items():
+        if "ms_per_step" in o:
+            o["img_s"] = o["global_batch"] * 1e3 / o["ms_per_step"]
+            o["whole_forward_tflops_per_gpu"] = o.pop("flops_per_image") * o["per_gpu_batch"] / (o["ms_per_step"] / 1e3) / 1e12
+            o["frac_of_burst_peak"] = o["whole_forward_tflops_per_gpu"] / peaks["burst"]
+            o["note"] = f"{o['steps']} eager steps after 3 warm-ups, device-resident, max over ranks"
 
     line = {
         "metric": "images_per_sec", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak" if CONFIGS[args.config][2] == "per_gpu" or args.batch else "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": desc, "arch": arch, "per_gpu_batch": batch, "global_batch": global_batch,
                    "tokens": N_tok, "parallelism": f"dp{world}" if world > 1 else "single",
                    "l2": f"{n_rot} distinct input batches rotated; per-step activation footprint > L2",
                    "weights": "random-init (trunc-normal 0.02), replicated",
-                   "gather": ("pooled CLS embeddings, " + dp.gather_impl) if world > 1 else "none (one GPU)"},
+                   "launch": run.note,
+                   "gather": ("pooled CLS embeddings, " + dp.gather_impl + ", pipelined (step i collects step i-1; "
+                              "the last step is drained inside the timed region)") if world > 1 else "none (one GPU)"},
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": "img/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": host_inputs[0].numel() * 2 * world,
                 "d2h_bytes_per_step": pooled_host.numel() * 2 * world,
                 "host_wall_ms_per_step": e2e_wall_ms / args.steps,
-                "api": "DataParallelVIT(model)(pixels) from pinned host bf16 pixels, double-buffered H2D",
+                "api": "DataParallelVIT(model) steps from pinned host bf16 pixels, double-buffered H2D, D2H of the "
+                       "gathered embeddings every step",
                 "uint8_nhwc": {"value": global_batch * args.steps / (e2e_u8_ms / 1e3), "unit": "img/s",
                                "ms_per_step": e2e_u8_ms / args.steps,
                                "h2d_bytes_per_step": host_u8[0].numel() * world,
@@ -422,6 +713,10 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    if check is not None:
+        line["gather_check"] = check
+    if others:
+        line["other_configs"] = others
     if world == 1 and not args.no_cpu_baseline:
         cpu_val, threads, times = hf_cpu_images_per_sec(arch, 32)
         line["cpu_baseline"] = {"value": cpu_val, "unit": "img/s", "cores": threads, "kind": "port",

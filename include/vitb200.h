@@ -156,18 +156,29 @@ int vt_conv2d(const void* input, const void* weight, const void* bias, void* out
 int vt_pool_cls(const void* x, void* out, int32_t B, int32_t D, int64_t batch_stride, int32_t dtype,
                 void* stream);
 
-/* K7 fused with its collective — pool + all-gather over peer memory in ONE kernel (no NCCL call):
- * rank `rank` stores the CLS rows of its B images into rows [rank*B, (rank+1)*B) of every peer's gather
- * buffer peer_out[p] ((world*B, D), P2P-mapped device pointers, e.g. torch symmetric memory), raises
- * the counter peer_flags[p][rank] and returns once peer_flags[rank][p] of every p has reached this
- * step's value.  peer_out / peer_flags are HOST arrays of `world` device pointers; flags are uint32
- * counters zeroed once before the first step; `epoch` = 1, 2, 3, ... must advance by one per call on
- * every rank, all ranks must pass the same B and D, and the caller alternates between two gather
- * buffers by the parity of epoch.  world <= 16.  A peer that never arrives traps the kernel after 120 s.
+/* K7 fused with its collective — pool + all-gather over peer memory in ONE kernel (no NCCL call).
+ * Rank `rank` stores the CLS rows of its B images into rows [rank*B, (rank+1)*B) of every peer's gather
+ * buffer and raises the counter peer_flags[p][rank] (PUT); the gathered (world*B, D) rows are copied from
+ * this rank's own gather buffer into out_local once peer_flags[rank][p] of every p shows the step (GET).
+ *   peer_out    HOST array of 4*world device pointers: [b*world + p] = gather buffer b (0..3) of rank p,
+ *               (world*B, D) each, P2P-mapped (e.g. torch symmetric memory); step e uses buffer e mod 4
+ *   peer_flags  HOST array of `world` device pointers to uint32[world] counters, zeroed once before step 1
+ *   ctrl        this rank's uint32[2] in device memory, zeroed once: [0] = steps completed, [1] = scratch.
+ *               The step number lives THERE, not in an argument: launches are identical from step to step
+ *               and can be captured into a CUDA graph.
+ *   mode        VT_PG_PUT | VT_PG_GET: synchronous all-gather of this step (returns once every peer's rows of
+ *               this step are in out_local); VT_PG_PUT: store + signal only, never waits; VT_PG_GET: collect
+ *               step (steps completed - lag) — after a PUT, lag 1 collects the PREVIOUS step (no rank waits
+ *               for a slower peer inside a step), lag 0 drains the last one.  x is ignored for GET alone,
+ *               out_local for PUT alone.
+ * All ranks must pass the same B, D, dtype and issue the same sequence of modes.  world <= 16.  A peer that
+ * never arrives traps the kernel after 120 s.
  * (New: the reference has no multi-GPU step; replaces vt_pool_cls + ncclAllGather.) */
+#define VT_PG_PUT 1
+#define VT_PG_GET 2
 int vt_pool_cls_allgather(const void* x, int32_t B, int32_t D, int64_t batch_stride, int32_t dtype,
                           void* const* peer_out, uint32_t* const* peer_flags, int32_t rank, int32_t world,
-                          uint32_t epoch, void* stream);
+                          uint32_t* ctrl, void* out_local, int32_t mode, int32_t lag, void* stream);
 
 #ifdef __cplusplus
 }

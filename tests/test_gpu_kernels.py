@@ -562,26 +562,76 @@ def test_gemm_row_stats_output():
 
 # ------------------------------------------------------------------------------- pool + peer all-gather (K7)
 def test_pool_cls_allgather_single_rank_protocol():
-    """vt_pool_cls_allgather with world = 1 (the rank is its own peer): rows land in the buffer of the
-    epoch's parity, the flag counter advances by blocks-per-peer each step, repeated steps do not hang."""
+    """vt_pool_cls_allgather with world = 1 (the rank is its own peer): the step counter lives in device
+    memory (identical launches step after step), rows land in gather buffer step mod 4 and in the local
+    output, the flag counter advances by blocks-per-peer each step; then the split PUT / GET form: GET
+    with lag 1 returns the step before the last PUT, lag 0 the last one."""
     import ctypes
     from vit.kernels import _lib
     B, N, D = 37, 5, 768
     flags = torch.zeros(1, dtype=torch.int32, device=dev())
-    bufs = torch.full((2, B, D), float("nan"), device=dev(), dtype=torch.bfloat16)
+    ctrl = torch.zeros(2, dtype=torch.int32, device=dev())
+    bufs = torch.full((4, B, D), float("nan"), device=dev(), dtype=torch.bfloat16)
+    out = torch.full((B, D), float("nan"), device=dev(), dtype=torch.bfloat16)
     flag_tab = (ctypes.c_void_p * 1)(flags.data_ptr())
+    out_tab = (ctypes.c_void_p * 4)(*[bufs[b].data_ptr() for b in range(4)])
+
+    def launch(x, o, mode, lag):
+        _lib.call("vt_pool_cls_allgather", _lib.ptr(x), B, D, x.stride(0) if x is not None else D, _lib.VT_BF16,
+                  ctypes.cast(out_tab, ctypes.c_void_p), ctypes.cast(flag_tab, ctypes.c_void_p), 0, 1,
+                  ctrl.data_ptr(), _lib.ptr(o), mode, lag, _lib.stream_ptr(bufs))
+
     seen = []
-    for epoch in (1, 2, 3):
+    for step in (1, 2, 3, 4, 5):
         x = torch.randn(B, N, D, device=dev()).bfloat16()
-        out_tab = (ctypes.c_void_p * 1)(bufs[epoch & 1].data_ptr())
-        _lib.call("vt_pool_cls_allgather", x.data_ptr(), B, D, x.stride(0), _lib.VT_BF16,
-                  ctypes.cast(out_tab, ctypes.c_void_p), ctypes.cast(flag_tab, ctypes.c_void_p), 0, 1, epoch,
-                  _lib.stream_ptr(x))
+        launch(x, out, _lib.VT_PG_PUT | _lib.VT_PG_GET, 0)
         torch.cuda.synchronize()
-        assert torch.equal(bufs[epoch & 1], x[:, 0, :])
+        assert torch.equal(out, x[:, 0, :]) and torch.equal(bufs[step & 3], x[:, 0, :])
+        assert ctrl.tolist() == [step, 0]
         seen.append(int(flags.item()))
-    assert seen[1] - seen[0] == seen[0] and seen[2] - seen[1] == seen[0] and seen[0] >= 1
-    with pytest.raises(_lib.KernelError):      # epoch 0 is reserved (flags start at zero)
+    assert all(b - a == seen[0] for a, b in zip(seen, seen[1:])) and seen[0] >= 1
+    # split form, continuing from step 5
+    xs = [torch.randn(B, N, D, device=dev()).bfloat16() for _ in range(3)]
+    launch(xs[0], None, _lib.VT_PG_PUT, 0)                 # step 6
+    launch(xs[1], None, _lib.VT_PG_PUT, 0)                 # step 7
+    launch(None, out, _lib.VT_PG_GET, 1)                   # collects step 6
+    torch.cuda.synchronize()
+    assert torch.equal(out, xs[0][:, 0, :]) and ctrl.tolist() == [7, 0]
+    launch(xs[2], None, _lib.VT_PG_PUT, 0)                 # step 8
+    launch(None, out, _lib.VT_PG_GET, 1)                   # collects step 7
+    torch.cuda.synchronize()
+    assert torch.equal(out, xs[1][:, 0, :])
+    launch(None, out, _lib.VT_PG_GET, 0)                   # drains step 8
+    torch.cuda.synchronize()
+    assert torch.equal(out, xs[2][:, 0, :])
+    with pytest.raises(_lib.KernelError):                  # PUT needs rows
+        launch(None, out, _lib.VT_PG_PUT | _lib.VT_PG_GET, 0)
+    with pytest.raises(_lib.KernelError):                  # GET needs somewhere to put them
+        launch(None, None, _lib.VT_PG_GET, 0)
+
+
+def test_pool_cls_allgather_graph_replay():
+    """The gather launch has no per-step argument: captured once into a CUDA graph, every replay is the
+    next step (world = 1)."""
+    import ctypes
+    from vit.kernels import _lib
+    B, N, D = 16, 3, 256
+    flags = torch.zeros(1, dtype=torch.int32, device=dev())
+    ctrl = torch.zeros(2, dtype=torch.int32, device=dev())
+    bufs = torch.zeros((4, B, D), device=dev(), dtype=torch.bfloat16)
+    out = torch.zeros((B, D), device=dev(), dtype=torch.bfloat16)
+    x = torch.randn(B, N, D, device=dev()).bfloat16()
+    flag_tab = (ctypes.c_void_p * 1)(flags.data_ptr())
+    out_tab = (ctypes.c_void_p * 4)(*[bufs[b].data_ptr() for b in range(4)])
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
         _lib.call("vt_pool_cls_allgather", x.data_ptr(), B, D, x.stride(0), _lib.VT_BF16,
-                  ctypes.cast(out_tab, ctypes.c_void_p), ctypes.cast(flag_tab, ctypes.c_void_p), 0, 1, 0,
-                  _lib.stream_ptr(x))
+                  ctypes.cast(out_tab, ctypes.c_void_p), ctypes.cast(flag_tab, ctypes.c_void_p), 0, 1,
+                  ctrl.data_ptr(), out.data_ptr(), _lib.VT_PG_PUT | _lib.VT_PG_GET, 0, _lib.stream_ptr(x))
+    for step in (1, 2, 3, 4, 5, 6):
+        x.copy_(torch.randn(B, N, D, device=dev()).bfloat16())
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, x[:, 0, :]) and torch.equal(bufs[step & 3], x[:, 0, :]) and ctrl.tolist() == [step, 0]

@@ -167,6 +167,41 @@ def _dp_worker(rank, world, port, total, out_dir):
         dist.destroy_process_group()
 
 
+def _dp_disagree_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dp = DataParallelVIT(_FakePooled())
+        x = torch.randn(4, 3, 4, 4)
+        # every rank claims a different global batch: the collective plan must refuse on EVERY rank
+        try:
+            dp(x, 8 + rank)
+            verdict = "no error"
+        except AssertionError as exc:
+            verdict = "assert: " + str(exc)
+        # ... and a consistent call afterwards still works (nothing is left half-built), also pipelined
+        got = dp(x, 8)
+        prev = dp.submit(x, 8)
+        last = dp.flush()
+        ok = prev is None and torch.equal(last, got) and got.shape == (8, 3) and dp.gather_impl == "torch.distributed"
+        with open(os.path.join(out_dir, f"verdict{rank}.txt"), "w") as f:
+            f.write(f"{verdict}|{ok}")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_plan_is_collective_gloo_world2(tmp_path):
+    """The gather plan (peer-store kernel or torch.distributed, and with which shapes) is agreed through one
+    all-reduce the first time a shape is seen: ranks that disagree on the global batch all raise."""
+    world = 2
+    mp.spawn(_dp_disagree_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        verdict, ok = open(tmp_path / f"verdict{r}.txt").read().split("|")
+        assert verdict.startswith("assert: Ranks disagree on the global batch"), verdict
+        assert ok == "True"
+
+
 @pytest.mark.parametrize("total", [8, 7])      # equal shards (single-buffer path) and ragged shards
 def test_data_parallel_gather_gloo_world2(tmp_path, total):
     world = 2

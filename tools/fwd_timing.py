@@ -29,7 +29,7 @@ with torch.no_grad():
     print(f"{arch} b{B}: eager {eager:.3f} ms, graph {graph:.3f} ms")
     # per-kernel breakdown
     evs = []
-    def hook(name, before):
+    def hook(name, before, args=None):
         ev = torch.cuda.Event(enable_timing=True); ev.record(); evs.append((name, before, ev))
     _lib.event_hook = hook
     m(x)

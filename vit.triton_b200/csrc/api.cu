@@ -13,7 +13,7 @@ int add_elementwise(const void*, const void*, void*, long long, int, cudaStream_
 int softmax_rows(const void*, void*, long long, int, long long, int, cudaStream_t);
 int pool_cls(const void*, void*, int, int, long long, int, cudaStream_t);
 int pool_cls_allgather(const void*, int, int, long long, int, void* const*, unsigned int* const*, int, int,
-                       unsigned int, cudaStream_t);
+                       unsigned int*, void*, int, int, cudaStream_t);
 int gemm_bf16_tcgen05(const void*, long long, const void*, long long, void*, long long, int,
                       const float*, const void*, long long, int, int, int, int, cudaStream_t);
 int gemm2_bf16_tcgen05(const void*, long long, const void*, long long, void*, long long, const float*,
@@ -188,10 +188,10 @@ int vt_pool_cls(const void* x, void* out, int32_t B, int32_t D, int64_t batch_st
 
 int vt_pool_cls_allgather(const void* x, int32_t B, int32_t D, int64_t batch_stride, int32_t dtype,
                           void* const* peer_out, uint32_t* const* peer_flags, int32_t rank, int32_t world,
-                          uint32_t epoch, void* stream) {
+                          uint32_t* ctrl, void* out_local, int32_t mode, int32_t lag, void* stream) {
   return vt::pool_cls_allgather(x, B, D, batch_stride, dtype, peer_out,
-                                reinterpret_cast<unsigned int* const*>(peer_flags), rank, world, epoch,
-                                S(stream));
+                                reinterpret_cast<unsigned int* const*>(peer_flags), rank, world,
+                                reinterpret_cast<unsigned int*>(ctrl), out_local, mode, lag, S(stream));
 }
 
 }  // extern "C"

@@ -372,44 +372,66 @@ __global__ void pool_cls_kernel(const T* __restrict__ x, T* __restrict__ out, in
 // ------------------------------------------------------------------------------------------
 // pool + all-gather over peer memory (K7): every rank stores the CLS rows of its images straight into
 // the gather buffer of every peer (NVLink P2P stores, 16 bytes per thread), then raises a counter in
-// that peer's flag array and waits until all peers have raised the counters in its own.  One kernel,
-// no NCCL call: the transfer is 393 KB per rank at C2, i.e. latency-bound, and the kernel saves the
+// that peer's flag array; the gathered rows are complete on a rank once every peer's counter in its own
+// flag array shows the step, and are then copied into a plain local output buffer.  One kernel, no
+// NCCL call: the transfer is 393 KB per rank at C2, i.e. latency-bound, and the kernel saves the
 // separate pool launch, the NCCL launch and its internal synchronisation.
 //
-// Protocol (per step, epoch e = 1, 2, ...; flags are monotonic counters, never reset):
-//   writer block (p, j) of rank r: copy its slice of rows to peer p, __syncthreads, thread 0:
-//       fence.sys + red.release.sys.add  flags_p[r] += 1
-//   reader: thread 0 of block (p, 0) spins (ld.acquire.sys) until flags_self[p] >= e * blocks_per_peer.
-// The gather buffers are double-buffered by the parity of e on the host side: a peer can only be one
-// epoch ahead (it waited for this rank's flag of epoch e before starting e + 1), so the buffer of
-// epoch e - 1, which this rank's stream may still be reading, is never written.
+// Protocol (step e = 1, 2, ...; flags are monotonic counters, never reset; ALL state is in device memory
+// — ctrl[0] = steps completed, ctrl[1] = block ticket — so a launch has no per-step argument and can be
+// captured into a CUDA graph and replayed):
+//   PUT  block (p, j) of rank r: e = ctrl[0] + 1; copy its slice of rows into peer p's buffer (e mod 4),
+//        __syncthreads, thread 0: fence.sys + red.release.sys.add  flags_p[r] += 1.
+//        The last block of the launch to finish (ticket) sets ctrl[0] = e.
+//   GET  block (p, j): e = ctrl[0] - lag; thread 0 spins (ld.acquire.sys) until
+//        flags_self[p] >= e * blocks_per_peer, then the block copies peer p's rows out of this rank's own
+//        buffer (e mod 4) into the local output.
+// PUT and GET are phases of ONE launch (mode PUT|GET: e is the step being put, the classic synchronous
+// all-gather) or two launches: PUT of step i followed by GET with lag = 1 collects step i - 1, whose
+// flags have long arrived, so no rank ever waits for a slower peer inside a step (the per-step barrier
+// is off the critical path); GET with lag = 0 drains the last step.
+// FOUR gather buffers are used in turn (e mod 4).  A peer can write step s into this rank's buffer once
+// its own GET of step s - 1 (synchronous mode) or s - 2 (lag 1) is done, i.e. once this rank has finished
+// PUT s - 1 / s - 2; this rank may then still have the GET of s - 1 (synchronous) or of s - 3 and s - 2
+// (lag 1: GET s - 3 directly follows PUT s - 2 in the stream) in front of it — steps s - 3 .. s are the
+// ones that can be live at once, anything older has been read.
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 16;
 struct PeerTable {
-  void* out[kMaxPeers];            // gather buffer of every rank (this epoch's), (world * batch, dim)
+  void* out[4][kMaxPeers];         // gather buffers of every rank, by step mod 4: (world * batch, dim) each
   unsigned int* flags[kMaxPeers];  // flag array of every rank, [world] counters
 };
+enum : int { PG_PUT = 1, PG_GET = 2 };
 
 __global__ void __launch_bounds__(512)
 pool_cls_allgather_kernel(const uint4* __restrict__ x, long long batch_stride_v, int batch, int dim_v,
-                          PeerTable peers, int rank, int world, int blocks_per_peer, unsigned int epoch,
-                          long long out_row0_v) {
-  const int p = blockIdx.x / blocks_per_peer;      // destination rank
+                          const __grid_constant__ PeerTable peers, int rank, int world, int blocks_per_peer,
+                          unsigned int* __restrict__ ctrl, uint4* __restrict__ out_local, int mode, unsigned int lag) {
+  const int p = blockIdx.x / blocks_per_peer;      // peer this block talks to
   const int j = blockIdx.x - p * blocks_per_peer;
-  uint4* dst = static_cast<uint4*>(peers.out[p]) + out_row0_v;
   const long long n = static_cast<long long>(batch) * dim_v;
-  for (long long i = static_cast<long long>(j) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<long long>(blocks_per_peer) * blockDim.x) {
-    const int b = static_cast<int>(i / dim_v);
-    const int c = static_cast<int>(i - static_cast<long long>(b) * dim_v);
-    dst[i] = x[b * batch_stride_v + c];
+  unsigned int done;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(ctrl) : "memory");
+  const unsigned int e = (mode & PG_PUT) ? done + 1u : done - lag;
+
+  if (mode & PG_PUT) {
+    uint4* dst = static_cast<uint4*>(peers.out[e & 3u][p]) + static_cast<long long>(rank) * n;
+    for (long long i = static_cast<long long>(j) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(blocks_per_peer) * blockDim.x) {
+      const int b = static_cast<int>(i / dim_v);
+      const int c = static_cast<int>(i - static_cast<long long>(b) * dim_v);
+      dst[i] = x[b * batch_stride_v + c];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(peers.flags[p] + rank) : "memory");
+    }
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(peers.flags[p] + rank) : "memory");
-    if (j == 0) {
-      const unsigned int target = epoch * static_cast<unsigned int>(blocks_per_peer);
+
+  if ((mode & PG_GET) && static_cast<int>(e) > 0) {
+    if (threadIdx.x == 0) {
+      const unsigned int target = e * static_cast<unsigned int>(blocks_per_peer);
       const unsigned int* mine = peers.flags[rank] + p;
       unsigned long long t0;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -427,6 +449,26 @@ pool_cls_allgather_kernel(const uint4* __restrict__ x, long long batch_stride_v,
         __nanosleep(64);
       }
     }
+    __syncthreads();
+    // peer p's rows have landed in this rank's buffer (written over NVLink: read them from L2, not L1)
+    const uint4* src = static_cast<const uint4*>(peers.out[e & 3u][rank]) + static_cast<long long>(p) * n;
+    uint4* dst = out_local + static_cast<long long>(p) * n;
+    for (long long i = static_cast<long long>(j) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(blocks_per_peer) * blockDim.x)
+      dst[i] = __ldcg(src + i);
+  }
+
+  if (mode & PG_PUT) {
+    // every block has read ctrl[0] before it takes a ticket, so the last ticket may advance the step
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int ticket = atomicAdd(ctrl + 1, 1u);
+      if (ticket == gridDim.x - 1) {
+        ctrl[1] = 0u;
+        __threadfence();
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(ctrl), "r"(e) : "memory");
+      }
+    }
   }
 }
 
@@ -434,18 +476,26 @@ pool_cls_allgather_kernel(const uint4* __restrict__ x, long long batch_stride_v,
 
 int pool_cls_allgather(const void* x, int batch, int dim, long long batch_stride, int dtype,
                        void* const* peer_out, unsigned int* const* peer_flags, int rank, int world,
-                       unsigned int epoch, cudaStream_t stream) {
-  if (!x || !peer_out || !peer_flags || batch <= 0 || dim <= 0 || world <= 0 || world > kMaxPeers ||
-      rank < 0 || rank >= world || epoch == 0)
+                       unsigned int* ctrl, void* out_local, int mode, int lag, cudaStream_t stream) {
+  if (!peer_out || !peer_flags || !ctrl || batch <= 0 || dim <= 0 || world <= 0 || world > kMaxPeers ||
+      rank < 0 || rank >= world || (mode & ~(PG_PUT | PG_GET)) || mode == 0 || lag < 0)
     return VT_ERR_ARG;
+  if ((mode & PG_PUT) && (!x || lag != 0)) return VT_ERR_ARG;
+  if ((mode & PG_GET) && !out_local) return VT_ERR_ARG;
   const int es = dtype == VT_F32 ? 4 : dtype == VT_BF16 ? 2 : 0;
   if (es == 0) return VT_ERR_DTYPE;
   const int per16 = 16 / es;
-  if ((dim % per16) || (batch_stride % per16) || (reinterpret_cast<uintptr_t>(x) & 15)) return VT_ERR_ALIGN;
+  if ((dim % per16) || (batch_stride % per16) || (reinterpret_cast<uintptr_t>(x) & 15) ||
+      (reinterpret_cast<uintptr_t>(out_local) & 15) || (reinterpret_cast<uintptr_t>(ctrl) & 7))
+    return VT_ERR_ALIGN;
   PeerTable t;
   for (int p = 0; p < world; ++p) {
-    if (!peer_out[p] || !peer_flags[p] || (reinterpret_cast<uintptr_t>(peer_out[p]) & 15)) return VT_ERR_ARG;
-    t.out[p] = peer_out[p];
+    if (!peer_flags[p]) return VT_ERR_ARG;
+    for (int b = 0; b < 4; ++b) {
+      void* o = peer_out[b * world + p];
+      if (!o || (reinterpret_cast<uintptr_t>(o) & 15)) return VT_ERR_ARG;
+      t.out[b][p] = o;
+    }
     t.flags[p] = peer_flags[p];
   }
   const int dim_v = dim / per16;
@@ -454,8 +504,8 @@ int pool_cls_allgather(const void* x, int batch, int dim, long long batch_stride
   if (blocks_per_peer < 1) blocks_per_peer = 1;
   if (blocks_per_peer > 8) blocks_per_peer = 8;
   pool_cls_allgather_kernel<<<world * blocks_per_peer, 512, 0, stream>>>(
-      static_cast<const uint4*>(x), batch_stride / per16, batch, dim_v, t, rank, world, blocks_per_peer,
-      epoch, static_cast<long long>(rank) * batch * dim_v);
+      static_cast<const uint4*>(x), batch_stride / per16, batch, dim_v, t, rank, world, blocks_per_peer, ctrl,
+      static_cast<uint4*>(out_local), mode, static_cast<unsigned int>(lag));
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -16,6 +16,8 @@ _lib: Optional[ctypes.CDLL] = None
 VT_F32 = 0
 VT_BF16 = 1
 VT_U8 = 2     # raw NHWC pixels of vt_patch_embed
+VT_PG_PUT = 1  # vt_pool_cls_allgather modes
+VT_PG_GET = 2
 
 _c_i32 = ctypes.c_int32
 _c_i64 = ctypes.c_int64
@@ -49,7 +51,7 @@ SIGNATURES = {
                   _c_i32, _c_i32, _c_ptr],
     "vt_pool_cls": [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i64, _c_i32, _c_ptr],
     "vt_pool_cls_allgather": [_c_ptr, _c_i32, _c_i32, _c_i64, _c_i32, _c_ptr, _c_ptr, _c_i32, _c_i32,
-                              ctypes.c_uint32, _c_ptr],
+                              _c_ptr, _c_ptr, _c_i32, _c_i32, _c_ptr],
 }
 
 
@@ -122,8 +124,9 @@ def i64x4(a, b, c, d):
 # Count of kernel launches issued through this module (bench.py reports it as gpu_launches).
 launch_count = 0
 
-# Optional profiling hook: event_hook(name, before: bool) is called on the launching thread right
-# before and right after a kernel is enqueued (bench.py records CUDA events there).
+# Optional profiling hook: event_hook(name, before: bool, args) is called on the launching thread right
+# before and right after a kernel is enqueued (bench.py records CUDA events there and reads the shapes
+# out of ``args``, the C-ABI argument tuple of the call).
 event_hook = None
 
 
@@ -131,9 +134,9 @@ def call(name: str, *args) -> None:
     global launch_count
     hook = event_hook
     if hook is not None:
-        hook(name, True)
+        hook(name, True, args)
     rc = getattr(load(), name)(*args)
     if hook is not None:
-        hook(name, False)
+        hook(name, False, args)
     launch_count += 1
     check(rc, name)

@@ -54,12 +54,17 @@ def all_gather_rows(local: torch.Tensor, total_rows: int, group=None) -> torch.T
 class PeerGather:
     """Pool + all-gather as one kernel over NVLink peer memory (``vt_pool_cls_allgather``).
 
-    Owns two symmetric gather buffers of (world * B_local, D) (alternated by the parity of the step,
-    see the protocol note in csrc/rowwise.cu) and one symmetric array of ``world`` uint32 flag
-    counters, all allocated and exchanged through ``torch.distributed._symmetric_memory``.
-    ``__call__(hidden)`` returns the (world * B_local, D) gathered CLS rows: a VIEW of the current
-    buffer, valid until the next-but-one call (copy it to keep it longer).  Not CUDA-graph capturable
-    (the epoch is a launch argument)."""
+    Owns four symmetric gather buffers of (world * B_local, D) used in turn (step mod 4, see the protocol
+    note in csrc/rowwise.cu), one symmetric array of ``world`` uint32 flag counters — allocated and
+    exchanged through ``torch.distributed._symmetric_memory`` — and, in plain device memory, the step
+    counter and two local (world * B_local, D) output buffers.  The step number lives in device memory,
+    so every launch has the same arguments: the kernels are CUDA-graph capturable.
+
+    ``__call__(hidden)``       synchronous all-gather of this step's CLS rows (PUT | GET in one launch).
+    ``put(hidden)``/``get()``  the split form: ``put`` stores + signals and never waits; ``get(lag=1)``
+                               collects the step before the last ``put`` (its flags arrived a whole
+                               forward ago, so no rank waits for a slower peer), ``get(lag=0)`` the last.
+    Results are views of two alternating local buffers: valid until the next-but-one collect."""
 
     def __init__(self, batch_local: int, dim: int, dtype: torch.dtype, device: torch.device, group=None):
         import torch.distributed._symmetric_memory as symm_mem
@@ -70,33 +75,53 @@ class PeerGather:
         self.rank = dist.get_rank(self.group)
         assert self.world <= 16, f"At most 16 peers, provided: {self.world}"
         self.batch_local, self.dim, self.dtype = batch_local, dim, dtype
-        self.bufs = symm_mem.empty((2, self.world * batch_local, dim), dtype=dtype, device=device)
+        self.bufs = symm_mem.empty((4, self.world * batch_local, dim), dtype=dtype, device=device)
         self.flags = symm_mem.empty((self.world,), dtype=torch.int32, device=device)
         self.flags.zero_()
         self._buf_handle = symm_mem.rendezvous(self.bufs, self.group)
         self._flag_handle = symm_mem.rendezvous(self.flags, self.group)
+        self.ctrl = torch.zeros((2,), dtype=torch.int32, device=device)
+        self.outs = torch.empty((2, self.world * batch_local, dim), dtype=dtype, device=device)
         torch.cuda.synchronize(device)
         dist.barrier(self.group)                       # every rank's flags are zero before anyone writes
         buf_bytes = self.bufs[0].numel() * self.bufs.element_size()
         base = [int(a) for a in self._buf_handle.buffer_ptrs]
-        self._out_tables = [(ctypes.c_void_p * self.world)(*[a + parity * buf_bytes for a in base])
-                            for parity in (0, 1)]
+        self._out_table = (ctypes.c_void_p * (4 * self.world))(*[a + b * buf_bytes for b in range(4) for a in base])
         self._flag_table = (ctypes.c_void_p * self.world)(*[int(a) for a in self._flag_handle.buffer_ptrs])
-        self.epoch = 0
+        self._collects = 0
+
+    def _launch(self, hidden: Optional[torch.Tensor], out: Optional[torch.Tensor], mode: int, lag: int) -> None:
+        _lib = self._lib
+        if hidden is not None:
+            assert hidden.is_cuda and hidden.dim() == 3, f"Expected CUDA (B, N, D) hidden states, provided: {tuple(hidden.shape)}"
+            assert hidden.shape[0] == self.batch_local and hidden.shape[2] == self.dim and hidden.dtype == self.dtype, \
+                f"PeerGather was built for ({self.batch_local}, *, {self.dim}) {self.dtype}, provided: {tuple(hidden.shape)} {hidden.dtype}"
+            assert hidden.stride(2) == 1 and hidden.stride(0) % 8 == 0
+        ref = hidden if hidden is not None else out
+        _lib.call("vt_pool_cls_allgather", _lib.ptr(hidden), self.batch_local, self.dim,
+                  hidden.stride(0) if hidden is not None else self.dim, _lib.dtype_code(ref),
+                  ctypes.cast(self._out_table, ctypes.c_void_p), ctypes.cast(self._flag_table, ctypes.c_void_p),
+                  self.rank, self.world, self.ctrl.data_ptr(), _lib.ptr(out), mode, lag, _lib.stream_ptr(ref))
+
+    def _next_out(self) -> torch.Tensor:
+        self._collects += 1
+        return self.outs[self._collects & 1]
 
     def __call__(self, hidden: torch.Tensor) -> torch.Tensor:
-        assert hidden.is_cuda and hidden.dim() == 3, f"Expected CUDA (B, N, D) hidden states, provided: {tuple(hidden.shape)}"
-        assert hidden.shape[0] == self.batch_local and hidden.shape[2] == self.dim and hidden.dtype == self.dtype, \
-            f"PeerGather was built for ({self.batch_local}, *, {self.dim}) {self.dtype}, provided: {tuple(hidden.shape)} {hidden.dtype}"
-        assert hidden.stride(2) == 1 and hidden.stride(0) % 8 == 0
-        self.epoch += 1
-        parity = self.epoch & 1
-        _lib = self._lib
-        _lib.call("vt_pool_cls_allgather", hidden.data_ptr(), self.batch_local, self.dim, hidden.stride(0),
-                  _lib.dtype_code(hidden), ctypes.cast(self._out_tables[parity], ctypes.c_void_p),
-                  ctypes.cast(self._flag_table, ctypes.c_void_p), self.rank, self.world, self.epoch,
-                  _lib.stream_ptr(hidden))
-        return self.bufs[parity]
+        out = self._next_out()
+        self._launch(hidden, out, self._lib.VT_PG_PUT | self._lib.VT_PG_GET, 0)
+        return out
+
+    def put(self, hidden: torch.Tensor) -> None:
+        self._launch(hidden, None, self._lib.VT_PG_PUT, 0)
+
+    def get(self, lag: int = 1) -> torch.Tensor:
+        out = self._next_out()
+        self._launch(None, out, self._lib.VT_PG_GET, lag)
+        return out
+
+
+_DTYPE_CODES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2, torch.uint8: 3}
 
 
 class DataParallelVIT(torch.nn.Module):
@@ -105,19 +130,24 @@ class DataParallelVIT(torch.nn.Module):
 
     def __init__(self, model: torch.nn.Module, group=None, peer_gather: Optional[bool] = None,
                  output: str = "pooled"):
-        """``output``: "pooled" gathers the CLS embeddings (B, D); "logits" gathers the class logits
-        (B, num_labels) of a model built with a classifier head (``VIT(num_labels=...)``).
+        """``output``: "pooled" gathers the CLS embeddings (B, D); "pooler" the HF pooler output
+        tanh(dense(CLS)) (B, D) of a model built with ``add_pooling_layer=True``; "logits" the class
+        logits (B, num_labels) of a model built with a classifier head (``VIT(num_labels=...)``).
         ``peer_gather``: None = use the fused pool + peer-store kernel whenever it applies (CUDA,
         NCCL group, equal shards, symmetric memory available; VT_PEER_GATHER=0 disables), True =
-        require it, False = always all-gather through torch.distributed."""
+        require it, False = always all-gather through torch.distributed.  Which one runs is decided
+        COLLECTIVELY the first time a (local batch, global batch, dtype) combination is seen: every rank
+        contributes what it wants and what it holds to one all-reduce, so either all ranks use the
+        peer-store kernel with identical shapes or none does."""
         super().__init__()
         self.model = model
         self.group = group
         self.peer_gather = peer_gather
-        assert output in ("pooled", "logits"), f"output must be 'pooled' or 'logits', provided: {output}"
+        assert output in ("pooled", "pooler", "logits"), f"output must be 'pooled', 'pooler' or 'logits', provided: {output}"
         self.output = output
-        self._peer = None          # PeerGather, built on first use for one (B_local, D, dtype)
-        self._peer_failed = False
+        self._peer = None          # PeerGather of the current plan
+        self._plans = {}           # (B_local, global_batch, dtype) -> PeerGather | None (= torch.distributed)
+        self._pending = False      # a put() whose rows have not been collected yet (pipelined form)
         self.gather_impl = "none"  # what the last forward used: "peer-store kernel" | "torch.distributed" | "none"
 
     @property
@@ -132,8 +162,20 @@ class DataParallelVIT(torch.nn.Module):
         return shard_bounds(global_batch, self.world_size, self.rank)
 
     def forward_local(self, x_local: torch.Tensor) -> torch.Tensor:
-        """Pooled embeddings (or logits) of this rank's images, (B_local, D | num_labels); no communication."""
-        return self.model.logits(x_local) if self.output == "logits" else self.model.pooled(x_local)
+        """Pooled embeddings (or pooler output / logits) of this rank's images, (B_local, D | num_labels); no
+        communication."""
+        if self.output == "logits":
+            return self.model.logits(x_local)
+        if self.output == "pooler":
+            return self.model.pooler_output(x_local)
+        return self.model.pooled(x_local)
+
+    def _rows(self, x_local: torch.Tensor) -> torch.Tensor:
+        """(B_local, *, D) tensor whose [:, 0, :] rows this rank contributes: the final hidden states for
+        "pooled" (the gather kernel pools them itself), the head's output as a one-token sequence otherwise."""
+        if self.output == "pooled":
+            return self.model.forward_uint8(x_local) if x_local.dtype == torch.uint8 else self.model(x_local)
+        return self.forward_local(x_local).unsqueeze(1)
 
     def forward(self, x_local: torch.Tensor, global_batch: Optional[int] = None) -> torch.Tensor:
         """x_local: this rank's shard of the global batch (as laid out by ``local_slice``).
@@ -141,49 +183,101 @@ class DataParallelVIT(torch.nn.Module):
         world = self.world_size
         if world == 1:
             return self.forward_local(x_local)
+        assert not self._pending, "forward() called with a submit() outstanding: call flush() first"
         if global_batch is None:
             global_batch = x_local.shape[0] * world
-        if self._wants_peer(x_local, global_batch):
-            if self.output == "logits":
-                hidden = self.model.logits(x_local).unsqueeze(1)      # (B_local, 1, num_labels): "CLS row" = the logits
-            else:
-                hidden = self.model.forward_uint8(x_local) if x_local.dtype == torch.uint8 else self.model(x_local)
-            peer = self._peer_for(hidden)
-            if peer is not None:
-                self.gather_impl = "peer-store kernel"
-                return peer(hidden.contiguous())
-            out = torch.empty((hidden.shape[0], hidden.shape[2]), device=hidden.device, dtype=hidden.dtype)
-            from .kernels import _lib
-            _lib.call("vt_pool_cls", hidden.data_ptr(), out.data_ptr(), hidden.shape[0], hidden.shape[2],
-                      hidden.stride(0), _lib.dtype_code(hidden), _lib.stream_ptr(hidden))
-            self.gather_impl = "torch.distributed"
-            return all_gather_rows(out, global_batch, self.group)
+        peer = self._plan(x_local, global_batch)
+        if peer is not None:
+            self.gather_impl = "peer-store kernel"
+            return peer(self._rows(x_local).contiguous())
         self.gather_impl = "torch.distributed"
         return all_gather_rows(self.forward_local(x_local), global_batch, self.group)
 
-    def _wants_peer(self, x_local: torch.Tensor, global_batch: int) -> bool:
-        if self.peer_gather is False or self._peer_failed:
+    # ------------------------------------------------------------------ pipelined form
+    def submit(self, x_local: torch.Tensor, global_batch: Optional[int] = None) -> Optional[torch.Tensor]:
+        """Pipelined steps: run this rank's forward, hand its rows to the peers (store + signal, never
+        waits) and return the gathered embeddings of the PREVIOUS ``submit`` (None for the first one) —
+        their flags arrived a whole forward ago, so no rank ever waits for a slower peer inside a step.
+        ``flush()`` returns the last step's.  Falls back to the synchronous gather (returning the CURRENT
+        step's result one call late) when the peer-store kernel does not apply."""
+        world = self.world_size
+        if global_batch is None:
+            global_batch = x_local.shape[0] * max(world, 1)
+        peer = self._plan(x_local, global_batch) if world > 1 else None
+        if peer is None:
+            prev = getattr(self, "_late", None)
+            self._late = self.forward(x_local, global_batch) if world > 1 else self.forward_local(x_local)
+            self._pending_late = True
+            return prev
+        assert self._peer is None or self._peer is peer or not self._pending, "flush() before changing the batch shape"
+        self._peer = peer
+        self.gather_impl = "peer-store kernel"
+        peer.put(self._rows(x_local).contiguous())
+        had = self._pending
+        self._pending = True
+        return peer.get(lag=1) if had else None
+
+    def flush(self) -> Optional[torch.Tensor]:
+        """Gathered embeddings of the last ``submit`` (None if nothing is outstanding)."""
+        if getattr(self, "_pending_late", False):
+            self._pending_late = False
+            out, self._late = self._late, None
+            return out
+        if not self._pending:
+            return None
+        self._pending = False
+        return self._peer.get(lag=0)
+
+    # ------------------------------------------------------------------ collective plan (cold path)
+    def _out_dim(self) -> int:
+        if self.output == "logits":
+            return self.model.classifier.weight.shape[1]
+        return int(getattr(self.model, "hidden_dim", 0))
+
+    def _local_want(self, x_local: torch.Tensor, global_batch: int) -> bool:
+        if self.peer_gather is False:
             return False
         if self.peer_gather is None and os.environ.get("VT_PEER_GATHER", "1") == "0":
             return False
         ok = x_local.is_cuda and global_batch == x_local.shape[0] * self.world_size and x_local.shape[0] > 0 \
             and dist.get_backend(self.group) == "nccl"
-        if ok and self.output == "logits":
-            ok = self.model.classifier.weight.shape[1] % 8 == 0      # 16-byte rows for the vector stores
-        if self.peer_gather is True:
-            assert ok, "peer_gather=True needs CUDA inputs, an NCCL group and equal shards"
-        return ok
+        return bool(ok and self._out_dim() % 8 == 0)             # 16-byte rows for the vector stores
 
-    def _peer_for(self, hidden: torch.Tensor) -> Optional[PeerGather]:
-        key = (hidden.shape[0], hidden.shape[2], hidden.dtype)
-        if self._peer is not None and (self._peer.batch_local, self._peer.dim, self._peer.dtype) == key:
-            return self._peer
-        # building the buffers is a collective: every rank gets here with the same key or none does
-        try:
-            self._peer = PeerGather(hidden.shape[0], hidden.shape[2], hidden.dtype, hidden.device, self.group)
-        except Exception as exc:   # symmetric memory unavailable (no P2P, old driver): use NCCL from now on
-            if self.peer_gather is True:
-                raise
-            warnings.warn(f"peer-memory gather unavailable ({exc!r}); falling back to NCCL all-gather")
-            self._peer, self._peer_failed = None, True
-        return self._peer
+    def _plan(self, x_local: torch.Tensor, global_batch: int) -> Optional[PeerGather]:
+        """PeerGather to use for this (local batch, global batch, dtype), or None = torch.distributed.
+        First use of a combination is a COLLECTIVE: one MIN and one MAX all-reduce over what every rank
+        wants and holds (a rank that disagrees on the batch, width or dtype would otherwise store outside
+        a peer's buffer or leave the others spinning in the kernel), then — if all agree on the kernel —
+        the symmetric-memory rendezvous, whose success is agreed on the same way."""
+        key = (x_local.shape[0], global_batch, x_local.dtype)
+        if key in self._plans:
+            return self._plans[key]
+        want = self._local_want(x_local, global_batch)
+        first = next(self.model.parameters(), None)
+        out_dtype = first.dtype if first is not None else x_local.dtype
+        mine = torch.tensor([int(want), x_local.shape[0], self._out_dim(), _DTYPE_CODES.get(out_dtype, 9), global_batch],
+                            dtype=torch.int64, device=x_local.device)
+        lo, hi = mine.clone(), mine.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+        lo, hi = lo.tolist(), hi.tolist()
+        assert lo[4] == hi[4], f"Ranks disagree on the global batch ({lo[4]} .. {hi[4]}): pass the same global_batch on every rank"
+        assert lo[2] == hi[2] and lo[3] == hi[3], "Ranks disagree on the output width / dtype of the model"
+        agreed = lo[0] == 1 and lo[1] == hi[1]
+        peer = None
+        if agreed:
+            err = None
+            try:
+                peer = PeerGather(x_local.shape[0], self._out_dim(), out_dtype, x_local.device, self.group)
+            except Exception as exc:   # symmetric memory unavailable (no P2P, old driver)
+                err = exc
+            ok = torch.tensor([0 if peer is None else 1], dtype=torch.int64, device=x_local.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                if peer is None:
+                    warnings.warn(f"peer-memory gather unavailable ({err!r}); all ranks use the torch.distributed all-gather")
+                peer = None
+        if self.peer_gather is True:
+            assert peer is not None, "peer_gather=True needs CUDA inputs, an NCCL group, equal shards on every rank and symmetric memory"
+        self._plans[key] = peer
+        return peer
