@@ -109,6 +109,35 @@ int vt_gemm_strided(const void* A, const void* B, void* C, const void* bias, int
                     const int64_t* sB, const int64_t* sC, float scale, int32_t gelu, int32_t dtype,
                     void* stream);
 
+/* Batched general GEMM on the tensor cores (tcgen05 + TMEM + TMA, 4-D tensor maps):
+ *   C[zo,zi] = act( scale * A[zo,zi] . B[zo,zi] + bias ) (+ residual[zo,zi]),  zo < batch_outer, zi < batch_inner
+ * A: bf16 [M, K] per batch, K contiguous; element strides sA = {outer, inner, row}.
+ * B: bf16; b_mn_major == 0: [N, K] per batch, K contiguous; != 0: [K, N] per batch, N contiguous (the layout
+ *    matmul3 receives) — consumed in place as an MN-major UMMA operand; sB = {outer, inner, row}.
+ *    Both batch strides 0 = one matrix shared by all batches (weights).
+ * C / residual: out_dtype (bf16 | f32) [M, N] per batch, sC = {outer, inner, row}; bias f32 [N] (nullable);
+ * act: 0 none, 1 exact-erf GELU, 2 tanh.  Any M, N, K; every A / B stride a multiple of 8 elements and
+ * both bases 16-byte aligned (pack with vt_pack_bf16 otherwise).
+ * Replaces matmul3's matmul_triton (vit/kernels/matmul3.py:111-156); with split fp32 operands
+ * (vt_pack_bf16, pieces = 3) also matmul_triton (vit/kernels/matmul.py:111-156) for the fp32 model, whose
+ * tl.dot (matmul.py:92) is a TF32 tensor-core product; with act = 2 the HF pooler dense + tanh the reference's
+ * loader maps (vit/utils.py:63-64). */
+int vt_bgemm(const void* A, const void* B, void* C, const float* bias, const void* residual, int32_t M, int32_t N,
+             int32_t K, int32_t batch_outer, int32_t batch_inner, const int64_t* sA, const int64_t* sB, const int64_t* sC,
+             int32_t b_mn_major, float scale, int32_t act, int32_t out_dtype, void* stream);
+
+/* Operand packing for vt_bgemm: src (src_dtype f32 | bf16) [rows, cols] per batch with ANY element strides
+ * s_src = {outer, inner, row, col} -> dst bf16 rows of pieces * cpad elements (s_dst = {outer, inner, row}),
+ * columns cols .. cpad-1 of every piece zero.  pieces == 1: plain conversion (transpose / pad).
+ * pieces == 3: x = hi + lo with hi = bf16(x), lo = bf16(x - hi), laid out [hi | hi | lo] (pattern 0, the A
+ * operand) or [hi | lo | hi] (pattern 1, the B operand): one bf16 GEMM over K' = 3 * cpad then accumulates
+ * a_hi b_hi + a_hi b_lo + a_lo b_hi in fp32 ("3 x bf16" fp32 product, ~2^-16 relative).
+ * pieces == 6: three-way split x = x1 + x2 + x3, A side [a1|a1|a2|a1|a2|a3], B side [b1|b2|b1|b3|b2|b1]: the six
+ * products of weight >= 2^-16, fp32-faithful. */
+int vt_pack_bf16(const void* src, int32_t src_dtype, void* dst, int32_t rows, int32_t cols, int32_t batch_outer,
+                 int32_t batch_inner, const int64_t* s_src, const int64_t* s_dst, int32_t cpad, int32_t pieces,
+                 int32_t pattern, void* stream);
+
 /* K3 — fused attention forward (tcgen05, flash style, no materialised scores), bf16, head dim 64.
  * q/k/v: [B, N, H*dh] views with common row / batch strides (e.g. slices of a fused-QKV buffer);
  * out: [B, N, H*dh].  Replaces the per-head matmul3 -> softmax -> matmul3 -> slice-assign chain

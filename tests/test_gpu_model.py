@@ -183,7 +183,82 @@ def test_c4_c5_architectures_bf16_match_hf(arch):
         got = model(x.to(DEV, torch.bfloat16)).float().cpu()
     assert torch.isfinite(got).all()
     assert _cos(got, want) >= 0.999, f"cosine {_cos(got, want)}"
-    assert (got - want).abs().max().item() <= 0.2, f"max-abs {(got - want).abs().max().item()}"
+    assert (got - want).abs().max().item() <= 0.15, f"max-abs {(got - want).abs().max().item()}"
+
+
+def _plant_outliers(hf, kind):
+    """Make a random-init HF model produce the activations real checkpoints have (and N(0, 1) inputs through
+    random weights do not): massive-activation channels in the residual stream and rows whose mean is
+    large against their spread."""
+    with torch.no_grad():
+        layers = hf.encoder.layer
+        D = layers[0].output.dense.bias.numel()
+        if kind in ("massive_channels", "both"):
+            # a few residual-stream channels pushed to +-40..150 by the MLP output bias of the first blocks
+            for i, (ch, v) in enumerate(((5, 60.0), (D // 2 + 3, -120.0), (D - 7, 150.0), (130 % D, -40.0))):
+                layers[min(i, len(layers) - 1) // 2].output.dense.bias[ch] += v
+        if kind in ("large_mean", "both"):
+            # every channel of every token shifted: |mean| / std of the rows entering block 0 is ~ 6 .. 8
+            hf.embeddings.position_embeddings += 4.0
+            layers[0].attention.output.dense.bias += 2.0
+    return hf
+
+
+@pytest.mark.parametrize("kind", ["massive_channels", "large_mean", "both"])
+@pytest.mark.parametrize("arch", ["tiny-b", "vit-b16-224"])
+def test_layernorm_folding_with_planted_outliers(arch, kind):
+    """The default-on LayerNorm fold (one launch chain: statistics out of the producing GEMM's epilogue,
+    normalisation in the consuming GEMM's) on a model with massive-activation channels and large-mean
+    rows: folded and unfolded forwards agree, and the fold is no further from HF fp32 than the unfolded
+    bf16 path is (the bf16 storage of the residual stream, not the fold, sets the error here)."""
+    from vit import vit as vit_mod
+    hf = _plant_outliers(hf_oracle.build_hf(arch, seed=0), kind)
+    model, _ = _build(arch, torch.bfloat16, hf)
+    x = hf_oracle.make_input(arch, 3)
+    want = hf_oracle.hf_forward(hf, x)
+    xd = x.to(DEV, torch.bfloat16)
+    try:
+        with torch.no_grad():
+            vit_mod.set_layernorm_folding(False)
+            plain = model(xd).float().cpu()
+            vit_mod.set_layernorm_folding(True, mlp=True)
+            folded = model(xd).float().cpu()
+    finally:
+        vit_mod.set_layernorm_folding(True, mlp=True)
+    assert torch.isfinite(folded).all()
+    e_plain = (plain - want).abs().max().item()
+    e_fold = (folded - want).abs().max().item()
+    # With every channel shifted by 4 .. 6 one bf16 ulp of the residual stream is 6 % of a row's spread: the two
+    # launch chains round a few values differently and that noise is amplified from block to block whichever
+    # way LayerNorm is computed (the kernel-level tests check the fold itself on |mean| / std up to 1000, bit
+    # for bit against fp32) — so here the bar is "as close to HF fp32 as the unfolded bf16 path", not equality.
+    floor = 0.9995 if kind == "massive_channels" else 0.995
+    assert _cos(folded, plain) >= floor, f"cosine folded vs unfolded {_cos(folded, plain)}"
+    assert _cos(folded, want) >= min(0.999, _cos(plain, want) - 5e-4), f"cosine {_cos(folded, want)} (unfolded {_cos(plain, want)})"
+    assert e_fold <= 1.5 * e_plain + 0.02, f"max-abs folded {e_fold} vs unfolded {e_plain}"
+
+
+def test_repack_after_data_write_needs_invalidate():
+    """Writes THROUGH ``param.data`` bump no version counter: ``VIT.invalidate_packed()`` is the documented
+    way to drop the packed / folded operands afterwards; the unfused path, which reads the
+    parameters directly, is the witness."""
+    from vit import vit as vit_mod
+    model, _ = _build("tiny-b", torch.bfloat16)
+    x = hf_oracle.make_input("tiny-b", 2).to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        before = model(x).clone()
+        for p_ in model.encoder.layer[0].intermediate.parameters():
+            p_.data.mul_(1.7)                                  # invisible to the caches
+        model.encoder.layer[1].layernorm_before.weight.data.mul_(0.5)
+        model.invalidate_packed()
+        after = model(x).clone()
+        vit_mod.set_fused(False)
+        try:
+            unfused = model(x)
+        finally:
+            vit_mod.set_fused(True)
+    assert not torch.equal(before, after)
+    assert _cos(after, unfused) >= 0.9995 and (after.float() - unfused.float()).abs().max().item() <= 0.1
 
 
 def test_uint8_nhwc_input_matches_hf_image_processor_path():
@@ -267,3 +342,43 @@ def test_classifier_head_matches_hf_image_classification():
             got = model.logits(x.to(DEV, dtype)).float().cpu()
         assert got.shape == want.shape == (5, 40)
         assert (got - want).abs().max().item() <= tol, f"{dtype}: max-abs {(got - want).abs().max().item()}"
+
+
+def test_reference_triton_forward_matches_ours(tmp_path):
+    """the reference's OWN forward (its VIT module, its Triton kernels, its loader,
+    unmodified, from baseline/_ref — see oracle/fetch_reference.sh) run on this GPU in a separate process,
+    compared with ours on the same weights and pixels.  Pins parity to the reference itself, not only to
+    HF.  Skipped when the copy is absent or the 2024 Triton source does not run under this Triton."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir(os.path.join(root, "baseline", "_ref", "vit")):
+        pytest.skip("baseline/_ref/vit absent (oracle/fetch_reference.sh runs in the build container)")
+    model, hf = _build("vit-b16-224", torch.float32)
+    x = hf_oracle.make_input("vit-b16-224", 2)
+    src, dst = str(tmp_path / "in.pt"), str(tmp_path / "out.pt")
+    torch.save({"state_dict": hf.state_dict(), "input": x}, src)
+    env = {k: v for k, v in os.environ.items() if k != "PYTHONPATH"}
+    proc = subprocess.run([sys.executable, os.path.join(root, "tools", "run_reference_triton.py"), src, dst, "32", "64"],
+                          env=env, capture_output=True, text=True, timeout=1500)
+    assert os.path.exists(dst), proc.stdout[-2000:] + proc.stderr[-2000:]
+    res = torch.load(dst)
+    out_dir = os.path.join(root, "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, "reference_triton.json"), "w") as f:
+        json.dump({"triton": res["triton"], "error": res["error"],
+                   "timings_ms": {str(k): v for k, v in res["timings_ms"].items()},
+                   "img_s": {str(k): k * 1e3 / v for k, v in res["timings_ms"].items()}}, f)
+    if res["error"] is not None:
+        pytest.skip("the reference did not run on this box: " + res["error"].strip().splitlines()[-1])
+    ref = res["output"]
+    want = hf_oracle.hf_forward(hf, x)
+    with torch.no_grad():
+        ours32 = model(x.to(DEV)).cpu()
+        ours16 = model.to(torch.bfloat16)(x.to(DEV, torch.bfloat16)).float().cpu()
+    # the reference multiplies in TF32 (tl.dot allow_tf32, matmul.py:92): ~3e-3 from HF fp32 (SURVEY.md 7.2)
+    assert (ref - want).abs().max().item() <= 2e-2, f"reference vs HF {(ref - want).abs().max().item()}"
+    assert (ours32 - ref).abs().max().item() <= 2e-2, f"ours fp32 vs reference {(ours32 - ref).abs().max().item()}"
+    assert (ours32 - want).abs().max().item() <= (ref - want).abs().max().item() + 1e-3     # at least as close to HF
+    assert _cos(ours16, ref) >= 0.999 and (ours16 - ref).abs().max().item() <= 0.15

@@ -30,6 +30,10 @@ int attn5mb_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, 
 int patch_embed_tcgen05(const void*, int, const void*, long long, const float*, void*, int, float*, int,
                         int, int, int, int, cudaStream_t);
 int patching(const void*, void*, int, int, int, int, int, int, cudaStream_t);
+int bgemm_tcgen05(const void*, const void*, void*, const float*, const void*, int, int, int, int, int, const long long*,
+                  const long long*, const long long*, int, float, int, int, cudaStream_t);
+int pack_bf16(const void*, int, void*, int, int, int, int, const long long*, const long long*, int, int, int,
+              cudaStream_t);
 int ln_fold(const void*, long long, const float*, const float*, const float*, void*, long long, float*, float*, int,
             int, int, cudaStream_t);
 int embed_finalize(void*, const void*, const void*, int, int, int, int, cudaStream_t);
@@ -129,6 +133,26 @@ int vt_gemm_strided(const void* A, const void* B, void* C, const void* bias, int
   for (int i = 0; i < 4; ++i) { a[i] = sA[i]; b[i] = sB[i]; c[i] = sC[i]; }
   return vt::simt_gemm(A, B, C, bias, M, N, K, batch_outer, batch_inner, a, b, c, scale, gelu,
                        dtype, S(stream));
+}
+
+int vt_bgemm(const void* A, const void* B, void* C, const float* bias, const void* residual, int32_t M, int32_t N,
+             int32_t K, int32_t batch_outer, int32_t batch_inner, const int64_t* sA, const int64_t* sB, const int64_t* sC,
+             int32_t b_mn_major, float scale, int32_t act, int32_t out_dtype, void* stream) {
+  if (!sA || !sB || !sC) return VT_ERR_ARG;
+  long long a[3], b[3], c[3];
+  for (int i = 0; i < 3; ++i) { a[i] = sA[i]; b[i] = sB[i]; c[i] = sC[i]; }
+  return vt::bgemm_tcgen05(A, B, C, bias, residual, M, N, K, batch_outer, batch_inner, a, b, c, b_mn_major, scale, act,
+                           out_dtype, S(stream));
+}
+
+int vt_pack_bf16(const void* src, int32_t src_dtype, void* dst, int32_t rows, int32_t cols, int32_t batch_outer,
+                 int32_t batch_inner, const int64_t* s_src, const int64_t* s_dst, int32_t cpad, int32_t pieces,
+                 int32_t pattern, void* stream) {
+  if (!s_src || !s_dst) return VT_ERR_ARG;
+  long long a[4], d[3];
+  for (int i = 0; i < 4; ++i) a[i] = s_src[i];
+  for (int i = 0; i < 3; ++i) d[i] = s_dst[i];
+  return vt::pack_bf16(src, src_dtype, dst, rows, cols, batch_outer, batch_inner, a, d, cpad, pieces, pattern, S(stream));
 }
 
 int vt_flash_attn(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H,

@@ -37,6 +37,10 @@ SIGNATURES = {
                         _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i32, _c_f32, _c_ptr, _c_ptr],
     "vt_gemm_strided": [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32,
                         _c_i64p, _c_i64p, _c_i64p, _c_f32, _c_i32, _c_i32, _c_ptr],
+    "vt_bgemm": [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _c_i64p, _c_i64p,
+                 _c_i64p, _c_i32, _c_f32, _c_i32, _c_i32, _c_ptr],
+    "vt_pack_bf16": [_c_ptr, _c_i32, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i64p, _c_i64p, _c_i32, _c_i32,
+                     _c_i32, _c_ptr],
     "vt_flash_attn": [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i64, _c_i64,
                       _c_i64, _c_i64, _c_f32, _c_ptr],
     "vt_patch_embed": [_c_ptr, _c_i32, _c_ptr, _c_i64, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32,
@@ -119,6 +123,10 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 def i64x4(a, b, c, d):
     return (ctypes.c_int64 * 4)(a, b, c, d)
+
+
+def i64x3(a, b, c):
+    return (ctypes.c_int64 * 3)(a, b, c)
 
 
 # Count of kernel launches issued through this module (bench.py reports it as gpu_launches).

@@ -1,15 +1,20 @@
 """Dense layer matmul — host entry point for K1 (replaces reference vit/kernels/matmul.py:111-156).
 
-Two device paths, chosen per call from dtype and alignment (one library, one architecture):
-  * bf16, K and N multiples of 8, rows of A dense  -> tcgen05/TMEM/TMA GEMM (``vt_gemm_bf16``)
-  * anything else (fp32, odd shapes, odd strides)  -> strided FP32-pipe GEMM (``vt_gemm_strided``)
+Device paths, chosen per call from dtype and alignment (one library, one architecture, all on tcgen05):
+  * bf16, K and N multiples of 8, rows of A dense  -> 2-CTA tcgen05/TMEM/TMA GEMM (``vt_gemm_bf16``)
+  * fp32                                           -> operands split into bf16 pieces (``vt_pack_bf16``),
+                                                      then the batched tcgen05 GEMM with fp32 output
+                                                      (``vt_bgemm``): fp32-faithful, see kernels/bgemm.py
+  * bf16 with odd shapes / strides                 -> one packing pass, then ``vt_bgemm``
+VT_EXACT_FP32=1 forces the strided FP32-pipe GEMM (``vt_gemm_strided``) for A/B comparisons.
 """
+import os
 import weakref
 from typing import Optional
 
 import torch
 
-from . import _lib
+from . import _lib, bgemm as bg
 
 # (id(tensor), tag) -> (weakref, (data_ptr, version), derived tensor).  Only nn.Parameters are cached: a plain
 # tensor's storage can be recycled by the allocator under the same pointer, a live Parameter's cannot.
@@ -89,12 +94,25 @@ def matmul(A: torch.Tensor, B: torch.Tensor, bias: Optional[torch.Tensor] = None
         return O
 
     assert A.dtype == B.dtype, f"Input dtypes need to be same, provided {A.dtype}, {B.dtype}"
-    if bias is not None and (bias.dtype != A.dtype or not bias.is_contiguous()):
-        bias = bias.to(A.dtype).contiguous()
-    _lib.call("vt_gemm_strided", A.data_ptr(), B.data_ptr(), O.data_ptr(), _lib.ptr(bias), M, N, K,
-              batch, 1,
-              _lib.i64x4(A.stride(0), 0, A.stride(1), A.stride(2)),
-              _lib.i64x4(0, 0, B.stride(0), B.stride(1)),
-              _lib.i64x4(M * N, 0, N, 1),
-              1.0, 1 if activation else 0, _lib.dtype_code(A), stream)
+    if os.environ.get("VT_EXACT_FP32") == "1":
+        if bias is not None and (bias.dtype != A.dtype or not bias.is_contiguous()):
+            bias = bias.to(A.dtype).contiguous()
+        _lib.call("vt_gemm_strided", A.data_ptr(), B.data_ptr(), O.data_ptr(), _lib.ptr(bias), M, N, K,
+                  batch, 1,
+                  _lib.i64x4(A.stride(0), 0, A.stride(1), A.stride(2)),
+                  _lib.i64x4(0, 0, B.stride(0), B.stride(1)),
+                  _lib.i64x4(M * N, 0, N, 1),
+                  1.0, 1 if activation else 0, _lib.dtype_code(A), stream)
+        return O
+
+    # tensor cores for everything else: pack A (any strides) and W^T into K-major bf16 rows — fp32 split
+    # into pieces whose products are accumulated in fp32 — then the batched tcgen05 GEMM
+    pieces = 1 if A.dtype == torch.bfloat16 else bg.split_pieces()
+    wp = _cached(B, f"packed{pieces}", lambda w: bg.pack(w, w.data_ptr(), N, K, 1, 1, (0, 0, w.stride(1), w.stride(0)),
+                                                        pieces, pattern=1)[0])
+    bias32 = None if bias is None else _cached(bias, "f32", lambda b: b.detach().float().contiguous())
+    a = bg.pack(A, A.data_ptr(), M, K, batch, 1, (A.stride(0), 0, A.stride(1), A.stride(2)), pieces, pattern=0)
+    kk = a.shape[2]
+    bg.bgemm(a.data_ptr(), wp.data_ptr(), O, O.data_ptr(), M, N, kk, batch, 1, (M * kk, 0, kk), (0, 0, kk),
+             (M * N, 0, N), bias32=bias32, act=bg.ACT_GELU if activation else bg.ACT_NONE)
     return O

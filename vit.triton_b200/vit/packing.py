@@ -16,7 +16,9 @@ from typing import Optional
 
 import torch
 
-from .kernels import _lib
+import os
+
+from .kernels import _lib, bgemm as bg
 
 
 class PackedMixin:
@@ -258,19 +260,48 @@ def linear(x: torch.Tensor, w_nk: torch.Tensor, bias32: torch.Tensor, gelu: bool
                   1 if gelu else 0, stream)
         return out
 
-    bias = bias32 if x.dtype == torch.float32 else bias32.to(x.dtype)
-    code = _lib.dtype_code(x)
-    step = 65535 * 64
-    for m0 in range(0, M, step):
-        mm = min(step, M - m0)
-        es = x.element_size()
-        _lib.call("vt_gemm_strided", x.data_ptr() + m0 * K * es, w_nk.data_ptr(),
-                  out.data_ptr() + m0 * n_out * es, bias.data_ptr(), mm, n_out, K, 1, 1,
-                  _lib.i64x4(0, 0, K, 1), _lib.i64x4(0, 0, 1, K), _lib.i64x4(0, 0, n_out, 1),
-                  1.0, 1 if gelu else 0, code, stream)
-    if residual is not None:
-        _lib.call("vt_add", out.data_ptr(), residual.data_ptr(), out.data_ptr(), out.numel(), code, stream)
+    if os.environ.get("VT_EXACT_FP32") == "1":      # FP32-pipe kernel, A/B comparisons only
+        bias = bias32 if x.dtype == torch.float32 else bias32.to(x.dtype)
+        code = _lib.dtype_code(x)
+        step = 65535 * 64
+        for m0 in range(0, M, step):
+            mm = min(step, M - m0)
+            es = x.element_size()
+            _lib.call("vt_gemm_strided", x.data_ptr() + m0 * K * es, w_nk.data_ptr(),
+                      out.data_ptr() + m0 * n_out * es, bias.data_ptr(), mm, n_out, K, 1, 1,
+                      _lib.i64x4(0, 0, K, 1), _lib.i64x4(0, 0, 1, K), _lib.i64x4(0, 0, n_out, 1),
+                      1.0, 1 if gelu else 0, code, stream)
+        if residual is not None:
+            _lib.call("vt_add", out.data_ptr(), residual.data_ptr(), out.data_ptr(), out.numel(), code, stream)
+        return out
+
+    # fp32 model (and bf16 layers whose widths are not multiples of 8): tensor cores through vt_bgemm —
+    # fp32 operands split into bf16 pieces (fp32-faithful, kernels/bgemm.py), bias / GELU / residual fused
+    pieces = 1 if x.dtype == torch.bfloat16 else bg.split_pieces()
+    wp = split_weight(w_nk, pieces)
+    bg.dense_rows(x, x.data_ptr(), M, K, K, wp, pieces, n_out, bias32, bg.ACT_GELU if gelu else bg.ACT_NONE, out,
+                  out.data_ptr(), n_out, residual_ptr=_lib.ptr(residual))
     return out
+
+
+# packed (split) forms of K-major weights, keyed on the packed tensor itself: the [N, K] matrices in the
+# PackedMixin namespaces are rebuilt (new tensors) whenever a source parameter changes, so entries die
+# with them
+_split_cache = {}
+
+
+def split_weight(w_nk: torch.Tensor, pieces: int) -> torch.Tensor:
+    key = (id(w_nk), pieces)
+    hit = _split_cache.get(key)
+    if hit is not None and hit[0]() is w_nk:
+        return hit[1]
+    import weakref
+    if len(_split_cache) > 1024:
+        for k in [k for k, v in _split_cache.items() if v[0]() is None]:
+            del _split_cache[k]
+    value = bg.pack_weight_nk(w_nk, pieces)
+    _split_cache[key] = (weakref.ref(w_nk), value)
+    return value
 
 
 def _embed_call(stats, b0, n_tok, dim, *args):
@@ -307,7 +338,8 @@ def patch_embed(emb, x: torch.Tensor, stats: Optional[torch.Tensor] = None) -> t
         return out
     assert stats is None, "Row statistics come out of the bf16 tensor-core patch embedding only"
 
-    # exact path: im2col rows, strided GEMM straight into rows 1..n of every image, then CLS/pos
+    # fp32 / odd-width path: im2col rows, tensor-core GEMM (fp32 operands split into bf16 pieces) straight
+    # into rows 1..n of every image, then CLS / position embeddings
     from .kernels.patching import patching
     if x.dtype != w.dtype:
         x = x.to(w.dtype)
@@ -316,13 +348,21 @@ def patch_embed(emb, x: torch.Tensor, stats: Optional[torch.Tensor] = None) -> t
     K = pk.K
     code = _lib.dtype_code(out)
     es = out.element_size()
-    bias = pk.bias32 if w.dtype == torch.float32 else emb.projection.bias.detach().contiguous()
-    for b0 in range(0, B, 32768):
-        nb = min(32768, B - b0)
-        _lib.call("vt_gemm_strided", patches[b0:].data_ptr(), pk.w.data_ptr(),
-                  out[b0:].data_ptr() + D * es, bias.data_ptr(), n, D, K, nb, 1,
-                  _lib.i64x4(n * K, 0, K, 1), _lib.i64x4(0, 0, 1, pk.ldw), _lib.i64x4(n_tok * D, 0, D, 1),
-                  1.0, 0, code, stream)
+    if os.environ.get("VT_EXACT_FP32") == "1":
+        bias = pk.bias32 if w.dtype == torch.float32 else emb.projection.bias.detach().contiguous()
+        for b0 in range(0, B, 32768):
+            nb = min(32768, B - b0)
+            _lib.call("vt_gemm_strided", patches[b0:].data_ptr(), pk.w.data_ptr(),
+                      out[b0:].data_ptr() + D * es, bias.data_ptr(), n, D, K, nb, 1,
+                      _lib.i64x4(n * K, 0, K, 1), _lib.i64x4(0, 0, 1, pk.ldw), _lib.i64x4(n_tok * D, 0, D, 1),
+                      1.0, 0, code, stream)
+    else:
+        pieces = 1 if w.dtype == torch.bfloat16 else bg.split_pieces()
+        wp = split_weight(pk.w, pieces)                    # [D, pieces * ldw]: pk.w rows are already padded to 8
+        a = bg.pack(patches, patches.data_ptr(), n, K, B, 1, (n * K, 0, K, 1), pieces, pattern=0)
+        kk = a.shape[2]
+        bg.bgemm(a.data_ptr(), wp.data_ptr(), out, out.data_ptr() + D * es, n, D, kk, B, 1, (n * kk, 0, kk),
+                 (0, 0, kk), (n_tok * D, 0, D), bias32=pk.bias32)
     _lib.call("vt_embed_finalize", out.data_ptr(), emb.position_embeddings.data_ptr(),
               emb.cls_token.data_ptr(), B, n_tok, D, code, stream)
     return out

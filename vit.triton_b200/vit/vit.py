@@ -286,20 +286,43 @@ class Embeddings(packing.PackedMixin, nn.Module):
         return packing.pack_embeddings(self)
 
 
+def _head_on_cls(hidden: torch.Tensor, dense: "LinearWithBias", act: int) -> torch.Tensor:
+    """(B, n_out) = act(dense(hidden[:, 0, :])): ONE tensor-core launch (``vt_bgemm``) that reads the CLS
+    rows in place through the row stride of its tensor map (no pooling kernel, no copy) and applies bias
+    and activation in the epilogue; fp32 models pack the rows into split bf16 pieces first."""
+    from .kernels import bgemm as bg
+    from .kernels.matmul import _cached
+    assert hidden.is_cuda and hidden.dim() == 3 and hidden.stride(2) == 1
+    B, _, D = hidden.shape
+    w = dense.weight                                       # (in, out)
+    n_out = w.shape[1]
+    out = torch.empty((B, n_out), device=hidden.device, dtype=hidden.dtype)
+    if B == 0:
+        return out
+    pieces = 1 if hidden.dtype == torch.bfloat16 else bg.split_pieces()
+    wp = _cached(w, f"packed{pieces}", lambda p_: bg.pack(p_, p_.data_ptr(), n_out, D, 1, 1,
+                                                          (0, 0, p_.stride(1), p_.stride(0)), pieces, pattern=1)[0])
+    bias32 = _cached(dense.bias, "f32", lambda b: b.detach().float().contiguous())
+    bg.dense_rows(hidden, hidden.data_ptr(), B, D, hidden.stride(0), wp, pieces, n_out, bias32, act, out,
+                  out.data_ptr(), n_out)
+    return out
+
+
 class Pooler(nn.Module):
     """HF ``ViTPooler`` (modeling_vit.py:461-474): tanh(dense(CLS hidden state)).  The reference's
     loader already maps ``pooler.dense.{weight,bias}`` (vit/utils.py:63-64) but the reference model has
-    no such module; ``VIT(..., add_pooling_layer=True)`` adds it.  The dense layer runs through the same
-    ``matmul`` entry point as every other dense layer (tensor-core GEMM for bf16); weight is (in, out)."""
+    no such module; ``VIT(..., add_pooling_layer=True)`` adds it.  On the GPU the dense layer and the tanh
+    are one tcgen05 GEMM launch with a tanh epilogue over the CLS rows (``_head_on_cls``); weight is (in, out)."""
 
     def __init__(self, hidden_dim: int):
         super().__init__()
         self.dense = LinearWithBias(hidden_dim, hidden_dim)
 
     def forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
-        cls = hidden_states[:, :1, :]                       # (B, 1, D) view: matmul takes any strides
-        out = self.dense(cls if cls.is_contiguous() else cls.contiguous())
-        return torch.tanh(out[:, 0, :])
+        if hidden_states.is_cuda:
+            from .kernels import bgemm as bg
+            return _head_on_cls(hidden_states, self.dense, bg.ACT_TANH)
+        return torch.tanh(self.dense(hidden_states[:, :1, :].contiguous())[:, 0, :])
 
 
 class VIT(nn.Module):
@@ -413,10 +436,12 @@ class VIT(nn.Module):
 
     def logits(self, x) -> torch.Tensor:
         """Class logits (B, num_labels) = classifier(final hidden states[:, 0]) — HF
-        ``ViTForImageClassification(...).logits``; needs ``VIT(..., num_labels=...)``."""
+        ``ViTForImageClassification(...).logits``; needs ``VIT(..., num_labels=...)``.  One tensor-core
+        launch over the CLS rows of the final hidden states."""
         assert self.classifier is not None, "VIT was built without a classifier head (num_labels)"
-        cls = self.pooled(x).unsqueeze(1)                  # (B, 1, D)
-        return self.classifier(cls)[:, 0, :]
+        hidden = self.forward_uint8(x) if x.dtype == torch.uint8 else self.forward(x)
+        from .kernels import bgemm as bg
+        return _head_on_cls(hidden, self.classifier, bg.ACT_NONE)
 
     def pooled(self, x) -> torch.Tensor:
         """CLS row of the final hidden states, (B, D): the tensor the data-parallel wrapper gathers.
