@@ -133,7 +133,7 @@ int vt_bgemm(const void* A, const void* B, void* C, const float* bias, const voi
  * operand) or [hi | lo | hi] (pattern 1, the B operand): one bf16 GEMM over K' = 3 * cpad then accumulates
  * a_hi b_hi + a_hi b_lo + a_lo b_hi in fp32 ("3 x bf16" fp32 product, ~2^-16 relative).
  * pieces == 6: three-way split x = x1 + x2 + x3, A side [a1|a1|a2|a1|a2|a3], B side [b1|b2|b1|b3|b2|b1]: the six
- * products of weight >= 2^-16, fp32-faithful. */
+ * products of weight >= 2^-16 (no more accurate than 3 pieces on B200: the fp32 accumulator truncates). */
 int vt_pack_bf16(const void* src, int32_t src_dtype, void* dst, int32_t rows, int32_t cols, int32_t batch_outer,
                  int32_t batch_inner, const int64_t* s_src, const int64_t* s_dst, int32_t cpad, int32_t pieces,
                  int32_t pattern, void* stream);

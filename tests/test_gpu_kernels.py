@@ -96,7 +96,9 @@ def test_matmul_fp32_exact(shape, act):
     want = a.double() @ b.double() + bias.double()
     if act:
         want = F.gelu(want)
-    assert (got.double() - want).abs().max().item() <= 1e-4 * max(1.0, math.sqrt(shape[1][0]) / 4)
+    # fp32 operands as six bf16 piece-products accumulated in fp32 on the tensor cores: 6 K adds per output,
+    # so sqrt(6) x the rounding noise of an fp32 FMA loop (values here reach +-100)
+    assert (got.double() - want).abs().max().item() <= 2.5e-4 * max(1.0, math.sqrt(shape[1][0]) / 4)
 
 
 def test_matmul_fp32_strided_input():
@@ -269,8 +271,8 @@ def test_matmul3_reference_shapes_on_tensor_cores(dtype, tol, shape):
 
 
 def test_fp32_matmul_split_accuracy(monkeypatch):
-    """fp32 ``matmul`` on the tensor cores: 6-piece split is fp32-faithful, 3-piece ~2^-16 per product
-    (SURVEY.md 7.2), both far inside what one TF32 pass (the reference's tl.dot) gives."""
+    """fp32 ``matmul`` on the tensor cores: the 3-piece split (default, ~2^-16 per product) and
+    the 6-piece one, both far inside what one TF32 pass (the reference's tl.dot, ~1e-3 here) gives."""
     from vit.kernels import matmul
     a = torch.randn(2, 197, 768, device=dev())
     w = torch.randn(768, 3072, device=dev()) / math.sqrt(768)
@@ -282,7 +284,10 @@ def test_fp32_matmul_split_accuracy(monkeypatch):
         errs[pieces] = (matmul(a, w, b, "gelu").double() - want).abs().max().item()
     monkeypatch.setenv("VT_EXACT_FP32", "1")
     errs["simt"] = (matmul(a, w, b, "gelu").double() - want).abs().max().item()
-    assert errs["6"] <= 5e-6 and errs["3"] <= 2e-4 and errs["simt"] <= 5e-6, errs
+    # measured on B200: 3 pieces 3.2e-5, 6 pieces 5.3e-5, FP32 pipe 6e-6.  The six-piece split is NOT better than
+    # the three-piece one on this hardware: the tensor core adds into its fp32 accumulator with truncation, and
+    # 6 K such adds lose more than the products dropped by the three-piece split
+    assert errs["6"] <= 1.5e-4 and errs["3"] <= 1.5e-4 and errs["simt"] <= 1e-5, errs
 
 
 # ------------------------------------------------------------------------------- attention (K3)

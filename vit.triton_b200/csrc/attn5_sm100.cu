@@ -20,10 +20,19 @@
 //   scores; O and the row sums (second N = 16 MMA against a tile of ones) are shared by both groups:
 //   PV_v is issued only after group (v-1) & 1 has read O_{v-1}, half a period earlier.
 //
-//   warps 0-7 / 8-15  softmax group 0 / 1: warp = 8 * group + 4 * column_half + row_quarter
+//   warps 0-7 / 8-15  softmax group 0 / 1: warp = 8 * group + 4 * column_half + row_quarter.  Per item:
+//                     wait S | row max + exchange | exp -> P | arrive P-ready — and straight on to the
+//                     group's next item.  They never touch O.
 //   warp 16           TMA producer (decodes the items into a shared-memory ring, allocates TMEM)
 //   warp 17           MMA issuer: per item v: wait P_v, V_v, O_{v-1} read | PV_v (+ row sums) |
 //                     S_{v+2} = Q K^T into S[v & 1]
+//   warps 18-21       epilogue (one per TMEM lane quarter), all items in order: wait O_v | read O + row
+//                     sum | release O | scale by 1 / sum, bf16, SWIZZLE_128B staging | TMA store.
+//                     Round 1 had the softmax warps do this: per group and item the chain was wait-S 360 /
+//                     row max 810 / exchange 140 / exp 2670 / wait-O 1000 / O read 170 / store 620 cycles,
+//                     i.e. 1790 cycles in which a group's MUFU-bound exp pass could not start (two groups
+//                     = 2885 cycles per item against 1664 of MUFU work); with the O path on its own warps
+//                     a group's period is wait-S + max + exp and the kernel runs against the MUFU pipe.
 //
 // Sequences longer than 208 keys and head dim 80 run attn5mb_fwd_kernel below (online softmax over KV blocks).
 #include "attn_softmax.cuh"
@@ -36,13 +45,14 @@ namespace {
 
 constexpr int kDH5 = 64;
 constexpr int kQTile5 = 128;
-constexpr int kThreads5 = (16 + 2) * 32;               // 576
+constexpr int kThreads5 = (16 + 2) * 32;               // 576: multi-block kernel (O accumulated by the softmax warps)
+constexpr int kThreads5s = (16 + 2 + 4) * 32;          // 704: single-block kernel (+ 4 epilogue warps)
 constexpr int kQBytes5 = kQTile5 * kDH5 * 2;           // 16 KB
 constexpr int kMaxN5 = 208;
 constexpr int kSCols5 = 208;                           // columns per score buffer
 constexpr int kOCol5 = 2 * kSCols5;                    // 416: O (64 columns) then the row sums (16 columns)
 constexpr int kLCol5 = kOCol5 + kDH5;                  // 480
-constexpr int kStageBytes5 = 32 * 32 * 2;              // per warp: 32 rows x 32 bf16 (SWIZZLE_64B)
+constexpr int kStageBytes5 = 32 * 64 * 2;              // per epilogue warp: 32 rows x 64 bf16 (SWIZZLE_128B)
 constexpr int kOnesBytes5 = 16 * 16 * 2;
 constexpr int kRing5 = 8;
 constexpr int kSmemLimit5 = 232448;
@@ -169,7 +179,7 @@ __device__ __forceinline__ void exp_groups5(uint32_t a, int nv, float scale_log2
   tmem_st_wait();
 }
 
-__global__ void __launch_bounds__(kThreads5, 1)
+__global__ void __maxnreg__(88)
 attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                  const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_o,
                  const Attn5Params p) {
@@ -178,13 +188,13 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int kv_bytes = p.bkv * kDH5 * 2;
-  // [Q0][Q1][K0][K1][V0][V1][staging 16 x 2 KB][ones][barriers][tmem slot][item ring][row max exchange]
+  // [Q0][Q1][K0][K1][V0][V1][staging 4 x 4 KB][ones][barriers][tmem slot][item ring][row max exchange]
   const uint32_t q_smem = smem_base;
   const uint32_t k_smem = q_smem + 2 * kQBytes5;
   const uint32_t v_smem = k_smem + 2 * kv_bytes;
   const int stage_off = 2 * kQBytes5 + 4 * kv_bytes;
   const uint32_t stage_smem = smem_base + stage_off;
-  const int ones_off = stage_off + 16 * kStageBytes5;
+  const int ones_off = stage_off + 4 * kStageBytes5;
   const uint32_t ones_smem = smem_base + ones_off;
   const int bar_off = ones_off + kOnesBytes5;
   const uint32_t bar_base = smem_base + bar_off;
@@ -200,7 +210,9 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
 
   if (warp_idx == 17 && lane == 0) {
     for (int i = 0; i < C_NBARS; ++i)
-      mbar_init(bar(i), (i == C_PFULL || i == C_PFULL + 1 || i == C_OREAD || i == C_PHALF || i == C_PHALF + 1) ? 8 : 1);
+      mbar_init(bar(i), (i == C_PFULL || i == C_PFULL + 1 || i == C_PHALF || i == C_PHALF + 1) ? 8
+                        : (i == C_OREAD)                                                       ? 4
+                                                                                               : 1);
     fence_barrier_init();
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_k);
@@ -357,6 +369,68 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     }
 #endif
 #undef VT_MTICK
+  } else if (warp_idx >= 18) {
+    // ------------------------------------------------------------------ epilogue warps (O path)
+    const int rq = warp_idx & 3;             // TMEM lane quarter this warp may read
+    const int ew = warp_idx - 18;            // staging tile
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(rq * 32) << 16);
+    const uint32_t stage_addr = stage_smem + ew * kStageBytes5;
+    uint8_t* stage_row = smem_gen + stage_off + ew * kStageBytes5 + lane * 128;
+    const int sw = lane & 7;                 // SWIZZLE_128B phase of this thread's staging row
+    for (int v = 0; v < n_items; ++v) {
+      const int b = v & 1;
+      const uint32_t ph = (static_cast<uint32_t>(v) >> 1) & 1u;
+      // the previous store out of my staging tile has long been read: check now, off the critical path
+      if (lane == 0) tma_store_wait_read<0>();
+      mbar_wait_lean5(bar(C_OFULL + b), ph);
+      tc_fence_after();
+      const int4 desc = ring[v & (kRing5 - 1)];   // (image, head, query tile)
+      const bool live = desc.z * kQTile5 + rq * 32 < p.N;      // warp-uniform
+      uint32_t pk[32];                            // my row's 64 output columns as bf16 pairs
+      if (live) {
+        uint32_t rl[8];
+        tmem_ld_32x8(t_lane + kLCol5, rl);        // every one of the 16 sum columns holds the row sum
+        uint32_t r[32];
+        tmem_ld_32x32(t_lane + kOCol5, r);
+        tmem_ld_wait();
+        float inv;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(__uint_as_float(rl[0])));
+        const float2 inv2 = make_float2(inv, inv);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float2 o = __fmul2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), inv2);
+          pk[i >> 1] = pack_bf16x2(o.x, o.y);
+        }
+        tmem_ld_32x32(t_lane + kOCol5 + 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float2 o = __fmul2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), inv2);
+          pk[16 + (i >> 1)] = pack_bf16x2(o.x, o.y);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(C_OREAD));   // O and the row sums are in registers: PV of the next item may go
+      if (!live) continue;
+      // stage this warp's [32 rows x 64 columns] as a SWIZZLE_128B tile and TMA-store it (the staging tile
+      // is free: lane 0 waited for the previous store above, the __syncwarp ordered that before these writes)
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj)
+        *reinterpret_cast<uint4*>(stage_row + ((jj ^ sw) << 4)) =
+            make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                     :
+                     : "l"(reinterpret_cast<uint64_t>(&tma_o)), "r"(stage_addr), "r"(desc.y * kDH5),
+                       "r"(desc.z * kQTile5 + rq * 32), "r"(desc.x)
+                     : "memory");
+        tma_store_commit();
+      }
+    }
+    if (lane == 0) tma_store_wait<0>();
   } else {
     // ------------------------------------------------------------------ softmax warps
     const int g = warp_idx >> 3;             // group = score buffer = item parity
@@ -364,9 +438,6 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     const int rq = warp_idx & 3;             // row quarter = TMEM lane group
     const int row_in_tile = rq * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(rq * 32) << 16);
-    const uint32_t stage_addr = stage_smem + warp_idx * kStageBytes5;
-    uint8_t* stage_row = smem_gen + stage_off + warp_idx * kStageBytes5 + lane * 64;
-    const int sw = (lane >> 1) & 3;          // SWIZZLE_64B phase of this thread's staging row
     const int bar_id = 1 + g * 4 + rq;       // named barrier of the two warps sharing these rows
     float* x_mine = xm + (g * 2 + half) * kQTile5 + row_in_tile;
     const float* x_other = xm + (g * 2 + (half ^ 1)) * kQTile5 + row_in_tile;
@@ -427,6 +498,8 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
           case 1: exp_groups5<1>(t_mine, nvr, p.scale_log2, m, bar(C_PHALF + g), lane); break;
           default: break;
         }
+        // the exchange slot is rewritten in this group's next item: both readers are past it (each reads
+        // before it arrives on the named barrier of the next item)
       }
       tc_fence_before();
       __syncwarp();
@@ -435,57 +508,7 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
 #endif
       if (lane == 0) mbar_arrive(bar(C_PFULL + g));
       VT_TICK5(3)
-
-      // the previous store out of my staging tile has long been read: check now, off the critical path
-      if (lane == 0) tma_store_wait_read<0>();
-      // O_v: my 32 output columns and the row sum
-      mbar_wait_lean5(bar(C_OFULL + g), ph);
-      VT_TICK5(4)
-      tc_fence_after();
-      uint32_t r[32];
-      uint32_t rl[8];
-      if (live) {
-        tmem_ld_32x32(t_lane + kOCol5 + half * 32, r);
-        tmem_ld_32x8(t_lane + kLCol5, rl);   // every one of the 16 sum columns holds the row sum
-        tmem_ld_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(C_OREAD));
-      VT_TICK5(5)
-      if (!live) continue;
-      float inv;
-      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(__uint_as_float(rl[0])));
-      // stage this warp's [32 rows x 32 columns] as a SWIZZLE_64B tile and TMA-store it (the staging
-      // tile is free: lane 0 waited for the previous store above, the __syncwarp after the O read
-      // ordered that before every lane's writes)
-      const float2 inv2 = make_float2(inv, inv);
-      auto scaled = [&](int i) {   // two output columns, one FMUL2
-        const float2 o = __fmul2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), inv2);
-        return pack_bf16x2(o.x, o.y);
-      };
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        uint4 o4;
-        o4.x = scaled(8 * jj + 0);
-        o4.y = scaled(8 * jj + 2);
-        o4.z = scaled(8 * jj + 4);
-        o4.w = scaled(8 * jj + 6);
-        *reinterpret_cast<uint4*>(stage_row + ((jj ^ sw) << 4)) = o4;
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                     :
-                     : "l"(reinterpret_cast<uint64_t>(&tma_o)), "r"(stage_addr),
-                       "r"(desc.y * kDH5 + half * 32), "r"(desc.z * kQTile5 + rq * 32), "r"(desc.x)
-                     : "memory");
-        tma_store_commit();
-      }
-      VT_TICK5(6)
     }
-    if (lane == 0) tma_store_wait<0>();
 #ifdef VT_ATTN5_DBG
     if (dbg_on && (warp_idx & 7) == 0 && lane == 0) {
       long long* d = p.dbg + (2LL * blockIdx.x + g) * 8;
@@ -969,7 +992,7 @@ int attn5_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, in
   p.scale_log2 = scale * 1.4426950408889634f;
   p.reverse = reverse;
   p.dbg = g_attn5_dbg;
-  const int smem = 1024 + 2 * kQBytes5 + 4 * p.bkv * kDH5 * 2 + 16 * kStageBytes5 + kOnesBytes5 + 8 * C_NBARS + 8 +
+  const int smem = 1024 + 2 * kQBytes5 + 4 * p.bkv * kDH5 * 2 + 4 * kStageBytes5 + kOnesBytes5 + 8 * C_NBARS + 8 +
                    16 * kRing5 + 2 * 2 * kQTile5 * 4;
   if (smem > kSmemLimit5) return VT_ERR_UNSUPPORTED;
 
@@ -981,7 +1004,7 @@ int attn5_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, in
   if (rc) return rc;
   rc = make_tmap_bf16_3d(&tv, v, cols, N, B, qkv_row_stride, qkv_batch_stride, kDH5, p.bkv, TMAP_SW_128);
   if (rc) return rc;
-  rc = make_tmap_bf16_3d(&to, out, cols, N, B, out_row_stride, out_batch_stride, 32, 32, TMAP_SW_64);
+  rc = make_tmap_bf16_3d(&to, out, cols, N, B, out_row_stride, out_batch_stride, kDH5, 32, TMAP_SW_128);
   if (rc) return rc;
 
   static int granted[kMaxDevices] = {0};
@@ -990,7 +1013,7 @@ int attn5_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, in
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long grid = p.total_items < sms ? p.total_items : sms;
-  attn5_fwd_kernel<<<static_cast<unsigned>(grid), kThreads5, smem, stream>>>(tq, tk, tv, to, p);
+  attn5_fwd_kernel<<<static_cast<unsigned>(grid), kThreads5s, smem, stream>>>(tq, tk, tv, to, p);
   return static_cast<int>(cudaGetLastError());
 }
 

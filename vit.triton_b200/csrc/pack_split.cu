@@ -8,8 +8,10 @@
 // "3 x bf16" form of an fp32 product (4.7e-5 on the final hidden states, where one TF32
 // pass — what the reference's tl.dot does, vit/kernels/matmul.py:92 — gives 3.1e-3).
 // pieces == 6 is the three-way split x = x1 + x2 + x3 (24 mantissa bits, i.e. all of fp32) with the six
-// products of weight >= 2^-16:  A side [a1|a1|a2|a1|a2|a3],  B side [b1|b2|b1|b3|b2|b1]  — fp32-faithful
-// (4.8e-6 on the final hidden states, the same as an fp32 FMA pipeline), the default of the fp32 model.
+// products of weight >= 2^-16:  A side [a1|a1|a2|a1|a2|a3],  B side [b1|b2|b1|b3|b2|b1]  — exact to 2^-24 in
+// exact arithmetic, but measured NO better than three pieces on B200 (5.3e-5 vs 3.2e-5 at K = 768): the
+// tensor core's fp32 accumulation truncates, and twice the K steps cost more than lo*lo recovers.  The fp32
+// model therefore uses three pieces (kernels/bgemm.py:split_pieces).
 // With pieces == 1 it is a plain (transposing, zero-padding) conversion: odd row lengths (197 keys) and
 // [K, N] operands of matmul3 (vit/kernels/matmul3.py:111-156) become K-major rows of a multiple of 8.
 #include "common.cuh"

@@ -17,10 +17,14 @@ _ACT = {None: ACT_NONE, "": ACT_NONE, "gelu": ACT_GELU, "tanh": ACT_TANH}
 
 
 def split_pieces() -> int:
-    """Pieces an fp32 operand is split into for the tensor cores: 6 = three-way split with six products
-    (fp32-faithful, default), 3 = two-way split with three products (~2^-16 per product, SURVEY.md 7.2);
-    VT_FP32_SPLIT=3 selects the cheaper form."""
-    return 3 if os.environ.get("VT_FP32_SPLIT", "6") == "3" else 6
+    """Pieces an fp32 operand is split into for the tensor cores: 3 (default) = x = hi + lo, three products
+    hi*hi + hi*lo + lo*hi (~2^-16 per product); 6 = three-way split with the six products
+    of weight >= 2^-16 (VT_FP32_SPLIT=6).  Measured on B200 (tests/test_gpu_kernels.py:
+    test_fp32_matmul_split_accuracy, K = 768): 3.2e-5 / 5.3e-5 max-abs for 3 / 6 pieces against 6e-6 on the
+    FP32 pipe and ~1e-3 for one TF32 pass — six pieces are NOT more accurate on this hardware, because the
+    tensor core adds into its fp32 accumulator with truncation and twice as many K steps lose more than
+    the dropped lo*lo products; hence the default."""
+    return 6 if os.environ.get("VT_FP32_SPLIT", "3") == "6" else 3
 
 
 def ceil8(n: int) -> int:

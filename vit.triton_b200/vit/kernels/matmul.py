@@ -4,7 +4,7 @@ Device paths, chosen per call from dtype and alignment (one library, one archite
   * bf16, K and N multiples of 8, rows of A dense  -> 2-CTA tcgen05/TMEM/TMA GEMM (``vt_gemm_bf16``)
   * fp32                                           -> operands split into bf16 pieces (``vt_pack_bf16``),
                                                       then the batched tcgen05 GEMM with fp32 output
-                                                      (``vt_bgemm``): fp32-faithful, see kernels/bgemm.py
+                                                      (``vt_bgemm``): ~2^-16 per product, see kernels/bgemm.py
   * bf16 with odd shapes / strides                 -> one packing pass, then ``vt_bgemm``
 VT_EXACT_FP32=1 forces the strided FP32-pipe GEMM (``vt_gemm_strided``) for A/B comparisons.
 """

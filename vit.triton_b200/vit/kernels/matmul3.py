@@ -15,7 +15,7 @@ def matmul3(A: torch.Tensor, B: torch.Tensor, apply_scaling: bool = False,
     (matmul3.py:97): bf16 operands whose rows are multiples of 8 elements are consumed IN PLACE — B as
     the (dim, dim_out) row-major matrix the caller passes, an MN-major UMMA operand, no transpose copy —
     other shapes go through one packing pass (``vt_pack_bf16``: zero-padded K-major rows); fp32 operands
-    are split into bf16 pieces first (fp32-faithful, see kernels/bgemm.py).  VT_EXACT_FP32=1 forces the
+    are split into bf16 pieces first (~2^-16 per product, see kernels/bgemm.py).  VT_EXACT_FP32=1 forces the
     FP32-pipe kernel (``vt_gemm_strided``) for A/B comparisons.
 
     The model's bf16 attention does not come through here (K3 fuses QK^T, softmax and PV); this entry

@@ -276,7 +276,7 @@ def linear(x: torch.Tensor, w_nk: torch.Tensor, bias32: torch.Tensor, gelu: bool
         return out
 
     # fp32 model (and bf16 layers whose widths are not multiples of 8): tensor cores through vt_bgemm —
-    # fp32 operands split into bf16 pieces (fp32-faithful, kernels/bgemm.py), bias / GELU / residual fused
+    # fp32 operands split into bf16 pieces (kernels/bgemm.py), bias / GELU / residual fused
     pieces = 1 if x.dtype == torch.bfloat16 else bg.split_pieces()
     wp = split_weight(w_nk, pieces)
     bg.dense_rows(x, x.data_ptr(), M, K, K, wp, pieces, n_out, bias32, bg.ACT_GELU if gelu else bg.ACT_NONE, out,
