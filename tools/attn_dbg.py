@@ -22,7 +22,7 @@ for (B, H, N, dh) in shapes:
     e.record()
     torch.cuda.synchronize()
     us = s.elapsed_time(e) / 20 * 1e3
-    dbg = torch.zeros(2 * 148 * 8, dtype=torch.int64, device="cuda")
+    dbg = torch.zeros(3 * 148 * 8, dtype=torch.int64, device="cuda")
     lib.vt_debug_set_attn_buffer(dbg.data_ptr())
     flash_attention(qkv, H)
     torch.cuda.synchronize()
@@ -30,16 +30,13 @@ for (B, H, N, dh) in shapes:
     nq = (N + 127) // 128
     impl = os.environ.get("VT_ATTN_IMPL", "5")
     print(f"B={B} H={H} N={N} dh={dh}: {us:.1f} us/launch (20 back-to-back)")
-    if impl == "4" and dh == 64:
-        d = dbg.view(296, 8)[:148].double()
-        n = B * H * nq / 148
-        names = ["wait-S", "load+max", "max-sync", "exp", "wait-O", "O-fold", "epilogue"]
-        print(f"   items/CTA {n:.1f}; per item cycles: " + ", ".join(f"{nm} {d[:, i].mean()/n:.0f}" for i, nm in enumerate(names))
-              + f", total {d[:, 7].mean()/n:.0f}")
-    else:
-        d = dbg.view(148, 2, 8).double()
-        n = B * H * nq / 296
-        names = ["wait-S", "pass1", "max-sync", "pass2", "wait-O", "O-read", "epilogue"]
-        for g in range(2):
-            print(f"   slot {g} per item cycles: " + ", ".join(f"{nm} {d[:, g, i].mean()/n:.0f}" for i, nm in enumerate(names))
-                  + f", total {d[:, g, 7].mean()/n:.0f}")
+    d = dbg[:2 * 148 * 8].view(148, 2, 8).double()
+    n = B * H * nq / 296
+    names = ["wait-S", "row max", "exchange", "exp", "wait-turn", "-", "-"]
+    for g in range(2):
+        print(f"   group {g} per item cycles: " + ", ".join(f"{nm} {d[:, g, i].mean()/n:.0f}" for i, nm in enumerate(names))
+              + f", total {d[:, g, 7].mean()/n:.0f}")
+    m = dbg[2 * 148 * 8:].view(148, 8).double()
+    ni = B * H * nq / 148
+    print("   MMA issuer per item cycles: " + ", ".join(f"{nm} {m[:, i].mean()/ni:.0f}" for i, nm in
+                                                       enumerate(["wait-V", "wait-O-read", "wait-P", "issue PV + S"])))

@@ -54,8 +54,16 @@ constexpr int kOCol5 = 2 * kSCols5;                    // 416: O (64 columns) th
 constexpr int kLCol5 = kOCol5 + kDH5;                  // 480
 constexpr int kStageBytes5 = 32 * 64 * 2;              // per epilogue warp: 32 rows x 64 bf16 (SWIZZLE_128B)
 constexpr int kOnesBytes5 = 16 * 16 * 2;
+constexpr int kOnesBytes5s = 16 * 128;                 // single-block kernel: 16 K rows x 128 B of ones (see the PV MMAs)
 constexpr int kRing5 = 8;
 constexpr int kSmemLimit5 = 232448;
+// -DVT_ATTN5_EXP_TURNS=1: the two softmax groups take strict turns on the MUFU pipe (experiment, measured no
+// faster: 73.9 vs 74.3 us per launch at C2 — an exp pass run ALONE by one group's 8 warps takes 2700 cycles,
+// as long as the other group's P -> PV -> S round trip + row-max pass that it would hide)
+#ifndef VT_ATTN5_EXP_TURNS
+#define VT_ATTN5_EXP_TURNS 0
+#endif
+constexpr bool kExpTurns5 = VT_ATTN5_EXP_TURNS != 0;
 
 struct Attn5Params {
   int N, H, B;
@@ -68,7 +76,9 @@ struct Attn5Params {
 };
 
 enum { C_QFULL = 0, C_QEMPTY = 2, C_KFULL = 4, C_KEMPTY = 6, C_VFULL = 8, C_VEMPTY = 10, C_SFULL = 12,
-       C_PFULL = 14, C_OFULL = 16, C_OREAD = 18, C_PHALF = 19, C_NBARS = 21 };
+       C_PFULL = 14, C_OFULL = 16, C_OREAD = 18, C_PHALF = 19, C_XTOK = 21, C_NBARS = 23 };
+// C_XTOK + g: the exp pass of group g's next item may start (the other group has finished the exp pass of the
+// item before it): the two groups take turns on the MUFU pipe, see the softmax warps of attn5_fwd_kernel.
 // C_PHALF (experiment, -DVT_ATTN5_SPLIT): the first (up to) four 16-column groups of every softmax
 // warp's P are in TMEM — the MMA issuer starts O = P V on those keys while the second part of the exp
 // pass is still running.  Measured SLOWER (79.6 vs 75.0 us per launch at C2): the mid-pass
@@ -179,7 +189,7 @@ __device__ __forceinline__ void exp_groups5(uint32_t a, int nv, float scale_log2
   tmem_st_wait();
 }
 
-__global__ void __maxnreg__(88)
+__global__ void __launch_bounds__(kThreads5s, 1)
 attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                  const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_o,
                  const Attn5Params p) {
@@ -196,7 +206,7 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   const uint32_t stage_smem = smem_base + stage_off;
   const int ones_off = stage_off + 4 * kStageBytes5;
   const uint32_t ones_smem = smem_base + ones_off;
-  const int bar_off = ones_off + kOnesBytes5;
+  const int bar_off = ones_off + kOnesBytes5s;
   const uint32_t bar_base = smem_base + bar_off;
   const uint32_t tmem_slot = bar_base + 8u * C_NBARS;
   const int slot_off = bar_off + 8 * C_NBARS;
@@ -210,17 +220,21 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
 
   if (warp_idx == 17 && lane == 0) {
     for (int i = 0; i < C_NBARS; ++i)
-      mbar_init(bar(i), (i == C_PFULL || i == C_PFULL + 1 || i == C_PHALF || i == C_PHALF + 1) ? 8
-                        : (i == C_OREAD)                                                       ? 4
-                                                                                               : 1);
+      mbar_init(bar(i), (i == C_PFULL || i == C_PFULL + 1 || i == C_PHALF || i == C_PHALF + 1 || i == C_XTOK ||
+                         i == C_XTOK + 1)       ? 8
+                        : (i == C_OREAD) ? 4
+                                         : 1);
     fence_barrier_init();
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_k);
     tma_prefetch_desc(&tma_v);
     tma_prefetch_desc(&tma_o);
   }
-  if (warp_idx == 0) {   // the tile of ones behind the row-sum MMAs (read through the async proxy)
-    reinterpret_cast<uint4*>(smem_gen + ones_off)[lane] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  if (warp_idx == 0) {   // the tile of ones behind the row sums (read through the async proxy)
+#pragma unroll
+    for (int i = 0; i < kOnesBytes5s / 16 / 32; ++i)
+      reinterpret_cast<uint4*>(smem_gen + ones_off)[lane + 32 * i] =
+          make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     fence_proxy_async_smem();
   }
   if (warp_idx == 16) {
@@ -315,17 +329,21 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       VT_MTICK(0)
       if (v > 0) mbar_wait(bar(C_OREAD), static_cast<uint32_t>(v - 1) & 1u);   // O columns free
       VT_MTICK(1)
-      const uint32_t idesc = make_idesc_bf16(kQTile5, kDH5, 0, 1);
-      const uint32_t idesc_l = make_idesc_bf16(kQTile5, 16, 0, 1);
-      const uint64_t vd = make_desc_mnmajor_sw128(v_smem + b * kv_bytes, 1024);
-      const uint64_t od = make_smem_desc(ones_smem, 256, 256, 6);   // every element is 1: layout is moot
+      // ONE MMA per 16 keys, N = 80: the B operand is MN-major with two 64-element groups, the V tile and —
+      // one leading-byte-offset further — a tile of ones whose first 16 columns give the row sums, which
+      // land in the 16 TMEM columns right behind O.  (Round 1 issued a second N = 16 MMA per step; the
+      // issuer spent 1489 cycles per item on 26 + 4 MMAs, ~50 each whatever their N, and the P -> PV -> S
+      // round trip is on each softmax group's critical path.)  The ones tile is 16 K rows x 128 B; every
+      // element is 1, so its swizzle is moot, and the per-step descriptor re-bases LBO onto it.
+      const uint32_t idesc = make_idesc_bf16(kQTile5, kDH5 + 16, 0, 1);
+      const uint32_t v_tile = v_smem + b * kv_bytes;
       const uint32_t s_tmem = tmem_base + b * kSCols5;
       // 16 keys: 8 packed P columns, 2048 B of V.  P of group k lives at the start of its owner's
       // columns: half 0 owns groups [0, ng0)
       auto pv_step = [&](int k, uint32_t acc) {
         const uint32_t a_tmem = s_tmem + (k < ng0 ? 8 * k : 16 * ng0 + 8 * (k - ng0));
-        umma_ts(tmem_base + kOCol5, a_tmem, vd + 128 * k, idesc, acc);
-        umma_ts(tmem_base + kLCol5, a_tmem, od, idesc_l, acc);
+        const uint32_t v_k = v_tile + 2048u * k;
+        umma_ts(tmem_base + kOCol5, a_tmem, make_desc_mnmajor_sw128(v_k, ones_smem - v_k), idesc, acc);
       };
 #ifdef VT_ATTN5_SPLIT
       // first part: the (up to) four leading groups of each column half, ready half-way through the exp pass
@@ -487,6 +505,10 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         named_bar_sync(bar_id, 64);
         const float m = fmaxf(mx, *x_other) * p.scale_log2;
         VT_TICK5(2)
+        // (experiment, off by default) the groups take turns on the MUFU pipe: item v's exp pass starts when
+        // item v - 1's (the other group's) is over
+        if (kExpTurns5 && v > 0) mbar_wait_lean5(bar(C_XTOK + g), static_cast<uint32_t>((v - 1) >> 1) & 1u);
+        VT_TICK5(4)
         // pass 2: exponentials; P overwrites my own consumed scores
         switch (ng) {
           case 7: exp_groups5<7>(t_mine, nvr, p.scale_log2, m, bar(C_PHALF + g), lane); break;
@@ -500,6 +522,12 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         }
         // the exchange slot is rewritten in this group's next item: both readers are past it (each reads
         // before it arrives on the named barrier of the next item)
+      } else if (kExpTurns5 && v > 0) {
+        mbar_wait_lean5(bar(C_XTOK + g), static_cast<uint32_t>((v - 1) >> 1) & 1u);   // keep the phase protocol
+      }
+      if (kExpTurns5) {   // hand the MUFU to the other group (item v + 1)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(C_XTOK + (g ^ 1)));
       }
       tc_fence_before();
       __syncwarp();
@@ -992,7 +1020,7 @@ int attn5_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, in
   p.scale_log2 = scale * 1.4426950408889634f;
   p.reverse = reverse;
   p.dbg = g_attn5_dbg;
-  const int smem = 1024 + 2 * kQBytes5 + 4 * p.bkv * kDH5 * 2 + 4 * kStageBytes5 + kOnesBytes5 + 8 * C_NBARS + 8 +
+  const int smem = 1024 + 2 * kQBytes5 + 4 * p.bkv * kDH5 * 2 + 4 * kStageBytes5 + kOnesBytes5s + 8 * C_NBARS + 8 +
                    16 * kRing5 + 2 * 2 * kQTile5 * 4;
   if (smem > kSmemLimit5) return VT_ERR_UNSUPPORTED;
 
