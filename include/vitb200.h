@@ -31,7 +31,7 @@ typedef enum {
   VT_ERR_DRIVER = -5       /* cuTensorMapEncodeTiled unavailable / failed */
 } vt_status;
 
-typedef enum { VT_F32 = 0, VT_BF16 = 1, VT_U8 = 2 /* pixels of vt_patch_embed only */ } vt_dtype;
+typedef enum { VT_F32 = 0, VT_BF16 = 1, VT_U8 = 2 /* pixels of vt_patch_embed only */, VT_E4M3 = 3 /* FP8 path only */ } vt_dtype;
 
 /* Library version (major*10000 + minor*100 + patch). */
 int vt_version(void);
@@ -108,6 +108,27 @@ int vt_gemm_strided(const void* A, const void* B, void* C, const void* bias, int
                     int32_t K, int32_t batch_outer, int32_t batch_inner, const int64_t* sA,
                     const int64_t* sB, const int64_t* sC, float scale, int32_t gelu, int32_t dtype,
                     void* stream);
+
+/* Optional FP8 path (off the bf16 headline metric) — K1 on tcgen05.mma kind::f8f6f4:
+ *   out[M,N] = act( (A8[M,K] . B8[N,K]^T) * colscale[n] + bias[n] ) (+ residual)
+ * A8, B8: e4m3 bytes, K-major, row strides lda / ldb in BYTES (multiples of 16, K % 16 == 0); colscale f32 [N] =
+ * per-output-channel weight scale x activation scale; bias f32 [N] (nullable); residual bf16 (nullable, ldr in elements);
+ * out_dtype VT_BF16 (ldo in elements) or VT_E4M3: out8 = e4m3(out * out_scale), ldo in bytes, N % 128 == 0, no residual.
+ * Replaces matmul_triton (vit/kernels/matmul.py:111-156) for the QKV / fc1 / fc2 layers when the FP8 path is on. */
+int vt_gemm_fp8(const void* A, int64_t lda, const void* Bt, int64_t ldb, void* out, int64_t ldo, int32_t out_dtype,
+                const float* bias, const float* colscale, const void* residual, int64_t ldr, int32_t M, int32_t N,
+                int32_t K, int32_t gelu, float out_scale, void* stream);
+
+/* K4 with the FP8 quantisation of the GEMM operand fused in: out8[m,:] = e4m3( LN(x[m,:]) * out_scale ), bf16 in
+ * (x, gamma, beta), e4m3 bytes out (row strides in elements / bytes).  layernorm_triton
+ * (vit/kernels/layernorm.py:90-127) for the FP8 path. */
+int vt_layernorm_fp8(const void* x, const void* gamma, const void* beta, void* out, int64_t rows, int32_t dim,
+                     int64_t in_row_stride, int64_t out_row_stride, float eps, float out_scale, void* stream);
+
+/* Pack-time weight quantisation: w bf16 [N,K] (row stride ldw elements) -> out8[n,:] = e4m3(w[n,:] / scales[n]),
+ * scales[n] = amax_k |w[n,k]| / 448 (1 for an all-zero row); ldo in bytes; K % 4 == 0. */
+int vt_quantize_rows_fp8(const void* w, int64_t ldw, void* out, int64_t ldo, float* scales, int32_t N, int32_t K,
+                         void* stream);
 
 /* Batched general GEMM on the tensor cores (tcgen05 + TMEM + TMA, 4-D tensor maps):
  *   C[zo,zi] = act( scale * A[zo,zi] . B[zo,zi] + bias ) (+ residual[zo,zi]),  zo < batch_outer, zi < batch_inner

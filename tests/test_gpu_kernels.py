@@ -744,3 +744,56 @@ def test_pool_cls_allgather_graph_replay():
         graph.replay()
         torch.cuda.synchronize()
         assert torch.equal(out, x[:, 0, :]) and torch.equal(bufs[step & 3], x[:, 0, :]) and ctrl.tolist() == [step, 0]
+
+
+# ------------------------------------------------------------------------------- FP8 path (VT_FP8, kind::f8f6f4)
+def _e4m3(t):
+    return t.to(torch.float8_e4m3fn)
+
+
+@pytest.mark.parametrize("M,N,K", [(197 * 3, 2304, 768), (300, 128, 3072), (129, 640, 1280), (64, 264, 512)])
+@pytest.mark.parametrize("mode", ["plain", "gelu", "res", "gelu_fp8out"])
+def test_gemm_fp8(M, N, K, mode):
+    """vt_gemm_fp8 against the same e4m3 operands multiplied in fp32 (the kernel's arithmetic is exact up to fp32
+    accumulation: products of e4m3 values are exact), column scales, bias, GELU, residual, e4m3 output."""
+    from vit import packing
+    if mode == "gelu_fp8out" and N % 128:
+        pytest.skip("e4m3 output needs N % 128 == 0")
+    x = torch.randn(1, M, K, device=dev())
+    w = (torch.randn(N, K, device=dev()) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=dev())
+    res = torch.randn(1, M, N, device=dev()).bfloat16()
+    x8 = _e4m3(x * 16.0)
+    w8, scales = packing.quantize_weight_fp8(w)
+    # the pack kernel's quantisation is the nearest-e4m3 rounding of w / (amax / 448)
+    want_w8 = _e4m3(w.float() / (w.float().abs().amax(dim=1, keepdim=True) / 448.0))
+    assert (w8.view(torch.float8_e4m3fn).float() != want_w8.float()).float().mean().item() <= 1e-3   # ties of w * (1 / s) vs w / s
+    assert torch.allclose(scales, w.float().abs().amax(dim=1) / 448.0)
+    colscale = (scales / 16.0).contiguous()
+    ref = (x8.float()[0] @ w8.view(torch.float8_e4m3fn).float().t()) * colscale + bias
+    got = packing.linear_fp8(x8.view(torch.uint8), w8, colscale, bias, gelu=mode.startswith("gelu"),
+                             residual=res if mode == "res" else None, out_fp8=mode == "gelu_fp8out", out_scale=8.0)
+    if mode.startswith("gelu"):
+        ref = F.gelu(ref)
+    if mode == "res":
+        ref = ref + res.float()[0]
+    if mode == "gelu_fp8out":
+        got = got.view(torch.float8_e4m3fn).float()[0] / 8.0
+        assert rel_err(got, ref) <= 0.04          # e4m3 rounding of the output: 2^-4 relative per element
+    else:
+        assert rel_err(got[0], ref) <= 2 ** -7, f"rel err {rel_err(got[0], ref)}"
+    # and the quantised product is a fair approximation of the bf16 layer itself
+    full = x[0] @ w.float().t() + bias
+    if mode == "plain":
+        assert rel_err(got[0], full) <= 0.06
+
+
+@pytest.mark.parametrize("rows,dim", [(197 * 2, 768), (77, 1024), (33, 1280), (5, 128)])
+def test_layernorm_fp8(rows, dim):
+    from vit import packing
+    x = (torch.randn(1, rows, dim, device=dev()) * 3 + 0.5).bfloat16()
+    ln = _ln_module(dim).to(torch.bfloat16)
+    got = packing.layernorm_fp8(x, ln).view(torch.float8_e4m3fn).float()[0] / 16.0
+    want = F.layer_norm(x.float()[0], (dim,), ln.weight.float(), ln.bias.float(), ln.eps)
+    assert (got - want).abs().max().item() <= 2 ** -4 * want.abs().max().item() + 1e-3
+    assert rel_err(got, want) <= 0.04

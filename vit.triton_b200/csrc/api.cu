@@ -34,6 +34,11 @@ int bgemm_tcgen05(const void*, const void*, void*, const float*, const void*, in
                   const long long*, const long long*, int, float, int, int, cudaStream_t);
 int pack_bf16(const void*, int, void*, int, int, int, int, const long long*, const long long*, int, int, int,
               cudaStream_t);
+int gemm2_fp8_tcgen05(const void*, long long, const void*, long long, void*, long long, int, const float*, const float*,
+                      const void*, long long, int, int, int, int, float, int, cudaStream_t);
+int layernorm_e4m3(const void*, const void*, const void*, void*, long long, int, long long, long long, float, float,
+                   cudaStream_t);
+int quantize_rows_e4m3(const void*, long long, void*, long long, float*, int, int, cudaStream_t);
 int ln_fold(const void*, long long, const float*, const float*, const float*, void*, long long, float*, float*, int,
             int, int, cudaStream_t);
 int embed_finalize(void*, const void*, const void*, int, int, int, int, cudaStream_t);
@@ -133,6 +138,24 @@ int vt_gemm_strided(const void* A, const void* B, void* C, const void* bias, int
   for (int i = 0; i < 4; ++i) { a[i] = sA[i]; b[i] = sB[i]; c[i] = sC[i]; }
   return vt::simt_gemm(A, B, C, bias, M, N, K, batch_outer, batch_inner, a, b, c, scale, gelu,
                        dtype, S(stream));
+}
+
+int vt_gemm_fp8(const void* A, int64_t lda, const void* Bt, int64_t ldb, void* out, int64_t ldo, int32_t out_dtype,
+                const float* bias, const float* colscale, const void* residual, int64_t ldr, int32_t M, int32_t N,
+                int32_t K, int32_t gelu, float out_scale, void* stream) {
+  if (out_dtype != VT_BF16 && out_dtype != VT_E4M3) return VT_ERR_DTYPE;
+  return vt::gemm2_fp8_tcgen05(A, lda, Bt, ldb, out, ldo, out_dtype == VT_E4M3, bias, colscale, residual, ldr, M, N, K,
+                               gelu, out_scale, next_direction(), S(stream));
+}
+
+int vt_layernorm_fp8(const void* x, const void* gamma, const void* beta, void* out, int64_t rows, int32_t dim,
+                     int64_t in_row_stride, int64_t out_row_stride, float eps, float out_scale, void* stream) {
+  return vt::layernorm_e4m3(x, gamma, beta, out, rows, dim, in_row_stride, out_row_stride, eps, out_scale, S(stream));
+}
+
+int vt_quantize_rows_fp8(const void* w, int64_t ldw, void* out, int64_t ldo, float* scales, int32_t N, int32_t K,
+                         void* stream) {
+  return vt::quantize_rows_e4m3(w, ldw, out, ldo, scales, N, K, S(stream));
 }
 
 int vt_bgemm(const void* A, const void* B, void* C, const float* bias, const void* residual, int32_t M, int32_t N,

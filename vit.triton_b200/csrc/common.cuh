@@ -23,7 +23,7 @@ enum : int {
   VT_ERR_DRIVER = -5,     // cuTensorMapEncode / driver entry point failure
 };
 
-enum : int { VT_F32 = 0, VT_BF16 = 1, VT_U8 = 2 };
+enum : int { VT_F32 = 0, VT_BF16 = 1, VT_U8 = 2, VT_E4M3 = 3 };
 
 // ----------------------------------------------------------------------------------------------
 // host: opt-in dynamic shared memory.  cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE

@@ -73,7 +73,11 @@ constexpr uint32_t kPeerMask = 0xFEFFFFFFu;             // clears the CTA-rank b
 
 // EPI_NOCS (with EPI_LNF): the folded weights have zero-sum rows (packing._fold_layernorm_zero_sum), so the
 // mean term is already inside the accumulator and the epilogue needs no column sums.
-enum : int { EPI_GELU = 1, EPI_RES = 2, EPI_LNF = 4, EPI_STATS = 8, EPI_NOCS = 16 };
+enum : int { EPI_GELU = 1, EPI_RES = 2, EPI_LNF = 4, EPI_STATS = 8, EPI_NOCS = 16, EPI_CSCALE = 32 };
+// EPI_CSCALE (FP8 operands): out = acc * colscale_n + bias_n — the per-output-channel dequantisation scale of the
+// e4m3 weights times the activation scale (Gemm2Params::colsum carries it).
+// PREC: 0 = bf16 operands, bf16 output (kind::f16); 1 = e4m3 operands, bf16 output; 2 = e4m3 operands, e4m3 output
+// (kind::f8f6f4: 128 K elements per 128-byte swizzle row, K = 32 per MMA, twice the MACs per operand byte).
 
 struct Gemm2Params {
   int M, N, K;
@@ -95,6 +99,7 @@ struct Gemm2Params {
   // Epilogue pacing (see the epilogue): cycles between the start slots of the tile's store bursts,
   // 0 = off; pace_q = additional stagger between the four lane-quarter warps of a slot
   int pace, pace_q;
+  float out_scale;   // PREC 2: multiplier applied before the e4m3 cast of the output
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -156,6 +161,32 @@ __device__ __forceinline__ void umma_ss_2cta(uint32_t d_tmem, uint64_t a_desc, u
       : "memory");
 }
 
+__device__ __forceinline__ void umma_ss_2cta_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Instruction descriptor for kind::f8f6f4 with e4m3 x e4m3 -> f32 (A / B format fields 0 = E4M3), K-major operands.
+__host__ __device__ constexpr uint32_t make_idesc_e4m3(int m, int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// four floats -> four e4m3 bytes (saturating), lowest address first
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+  uint16_t lo, hi;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+  return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+}
+
 // Arrive (once all prior MMAs of this thread completed) on the barrier at this offset in BOTH CTAs.
 __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
   const uint16_t mask = 3;
@@ -178,7 +209,7 @@ __device__ __forceinline__ float2 gelu_epi2(float2 x) { return gelu_erf_bf16_x2(
 __device__ __forceinline__ float2 gelu_epi2(float2 x) { return gelu_erf_poly_x2(x); }
 #endif
 
-template <int EPI, typename Cfg>
+template <int EPI, typename Cfg, int PREC = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const __grid_constant__ CUtensorMap tma_out,
@@ -187,6 +218,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   constexpr int kStageBufs = Cfg::kStageBufs;
   constexpr int kEpiBytes = Cfg::kEpiBytes;
   constexpr int kNumBars = Cfg::kNumBars;
+  constexpr bool kFp8In = PREC != 0;
+  constexpr bool kFp8Out = PREC == 2;
+  constexpr int kBKE = kFp8In ? 2 * BK : BK;       // K ELEMENTS per 128-byte operand row
+  static_assert(!kFp8Out || (kStageBufs == 1 && !(EPI & (EPI_RES | EPI_STATS | EPI_LNF))), "e4m3 output: plain / GELU epilogue");
+  static_assert(!(EPI & EPI_CSCALE) || !(EPI & EPI_LNF), "column scales and the LayerNorm fold do not combine");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -243,7 +279,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   const uint32_t tmem_base = *tmem_slot_gen;
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_kb = (p.K + kBKE - 1) / kBKE;
   long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long dbg_t0 = p.dbg ? clock64() : 0;
   const int first_tile = static_cast<int>(cluster_id_x());
@@ -270,8 +306,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         const uint32_t b_dst = a_dst + kABytes;
         if (elect_one_sync()) {
           if (is_leader) mbar_arrive_expect_tx(full_bar(s), 2 * kStageBytes);
-          tma_load_2d_2cta(&tma_a, full_bar(s), a_dst, kb * BK, a_row, kEvictNormal);
-          tma_load_2d_2cta(&tma_b, full_bar(s), b_dst, kb * BK, b_row, kEvictLast);
+          tma_load_2d_2cta(&tma_a, full_bar(s), a_dst, kb * kBKE, a_row, kEvictNormal);
+          tma_load_2d_2cta(&tma_b, full_bar(s), b_dst, kb * kBKE, b_row, kEvictLast);
         }
         __syncwarp();
         if (++s == kStages) { s = 0; phase ^= 1u; }
@@ -283,7 +319,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     // made the compiler wrap every UTCHMMA in an ELECT / R2UR.BROADCAST loop — ~19 instructions
     // per MMA — and the GELU epilogue then starved the issuer: tensor pipe 56 % instead of 80 %.)
     if (is_leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+      constexpr uint32_t idesc = kFp8In ? make_idesc_e4m3(2 * BM, BN) : make_idesc_bf16(2 * BM, BN, 0, 0);
       int s = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -307,8 +343,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             const uint64_t bdesc = make_desc_kmajor_sw128(b_src);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              // advancing K by 16 bf16 = 32 bytes = 2 units of the 16-byte start-address field
-              umma_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              // advancing K by 16 bf16 (32 e4m3) = 32 bytes = 2 units of the 16-byte start-address field
+              if (kFp8In) umma_ss_2cta_f8(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit_2cta(empty_bar(s));
           }
@@ -366,6 +403,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const bool in = cb + 3 < p.N;              // N % 8 == 0: groups of 4 are all in or all out
       b4n = (p.bias != nullptr && in) ? __ldg(reinterpret_cast<const float4*>(p.bias + cb))
                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (EPI & EPI_CSCALE)
+        c4n = in ? __ldg(reinterpret_cast<const float4*>(p.colsum + cb)) : make_float4(0.f, 0.f, 0.f, 0.f);
       if (EPI & EPI_LNF) {
         if (!(EPI & EPI_NOCS))
           c4n = in ? __ldg(reinterpret_cast<const float4*>(p.colsum + cb)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -470,7 +509,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       for (int c = 0; c < kChunks; ++c) {
         const int col = col0 + c * kChunkCols;
         const bool live = col < p.N;   // warp-uniform: chunk not entirely right of the matrix
-        if (kStageBufs < kChunks && c >= kStageBufs) {
+        if (!kFp8Out && kStageBufs < kChunks && c >= kStageBufs) {
           // the staging buffer is shared with an earlier chunk of this tile: its store must have read it
           if (lane == 0) {
             tma_store_wait_read<0>();
@@ -494,6 +533,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           // bias (and folded-LayerNorm term) of these 32 columns, broadcast from the owning lanes
           // while the TMEM load is in flight
           float4 bv[8];
+          float4 cv[(EPI & EPI_CSCALE) ? 8 : 1];
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const int src = 16 * c + 8 * hh + g;
@@ -501,6 +541,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             bv[g].y = __shfl_sync(0xffffffffu, b4.y, src);
             bv[g].z = __shfl_sync(0xffffffffu, b4.z, src);
             bv[g].w = __shfl_sync(0xffffffffu, b4.w, src);
+            if (EPI & EPI_CSCALE) {
+              cv[g].x = __shfl_sync(0xffffffffu, c4.x, src);
+              cv[g].y = __shfl_sync(0xffffffffu, c4.y, src);
+              cv[g].z = __shfl_sync(0xffffffffu, c4.z, src);
+              cv[g].w = __shfl_sync(0xffffffffu, c4.w, src);
+            }
             if ((EPI & EPI_LNF) && !(EPI & EPI_NOCS)) {
               float4 cs;
               cs.x = __shfl_sync(0xffffffffu, c4.x, src);
@@ -535,7 +581,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
               const float4 b0 = bv[2 * jj], b1 = bv[2 * jj + 1];
               const float2 bp[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
                                     make_float2(b1.z, b1.w)};
-              if (EPI & EPI_LNF) {
+              if (EPI & EPI_CSCALE) {
+                const float4 c0 = cv[2 * jj], c1 = cv[2 * jj + 1];
+                const float2 cp[4] = {make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y),
+                                      make_float2(c1.z, c1.w)};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = __ffma2_rn(v[q], cp[q], bp[q]);
+              } else if (EPI & EPI_LNF) {
                 const float2 a2 = make_float2(ln_a, ln_a);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) v[q] = __ffma2_rn(v[q], a2, bp[q]);
@@ -565,12 +617,25 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
                 st_sq2 = __ffma2_rn(d, d, st_sq2);
               }
             }
-            uint4 o4;
-            o4.x = pack_bf16x2(v[0].x, v[0].y);
-            o4.y = pack_bf16x2(v[1].x, v[1].y);
-            o4.z = pack_bf16x2(v[2].x, v[2].y);
-            o4.w = pack_bf16x2(v[3].x, v[3].y);
-            *slot = o4;
+            if (kFp8Out) {
+              // e4m3 output: the warp's 128 columns are ONE 128-byte staging row (32 rows x 128 B, SWIZZLE_128B);
+              // these eight columns are half of the 16-byte group (c * 4 + hh * 2 + jj / 2)
+              const float2 os = make_float2(p.out_scale, p.out_scale);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) v[q] = __fmul2_rn(v[q], os);
+              uint2 o2;
+              o2.x = pack_e4m3x4(v[0].x, v[0].y, v[1].x, v[1].y);
+              o2.y = pack_e4m3x4(v[2].x, v[2].y, v[3].x, v[3].y);
+              uint8_t* row8 = stage_gen[0] + lane * 128;
+              *reinterpret_cast<uint2*>(row8 + (((c * 4 + hh * 2 + (jj >> 1)) ^ sw) << 4) + ((jj & 1) << 3)) = o2;
+            } else {
+              uint4 o4;
+              o4.x = pack_bf16x2(v[0].x, v[0].y);
+              o4.y = pack_bf16x2(v[1].x, v[1].y);
+              o4.z = pack_bf16x2(v[2].x, v[2].y);
+              o4.w = pack_bf16x2(v[3].x, v[3].y);
+              *slot = o4;
+            }
           }
         }
         if ((EPI & EPI_STATS) && c == kChunks - 1) {
@@ -582,7 +647,16 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             *dst = make_float2(fmaf(-128.0f, st_npiv2.x, s_sh), fmaxf(fmaf(-s_sh * (1.0f / 128.0f), s_sh, q_sh), 0.f));
           }
         }
-        if (live) {
+        if (kFp8Out) {
+          if (c == kChunks - 1 && col0 < p.N) {     // one store of the warp's 128 e4m3 columns (N % 128 == 0, host)
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tma_out, stage_buf[0], col0, row0);
+              tma_store_commit();
+            }
+          }
+        } else if (live) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -630,10 +704,10 @@ int num_sms2() {
   return g_num_sms2;
 }
 
-template <int EPI, typename Cfg>
+template <int EPI, typename Cfg, int PREC = 0>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
             const CUtensorMap& tr, const Gemm2Params& p, cudaStream_t stream) {
-  auto kern = gemm2_bf16_kernel<EPI, Cfg>;
+  auto kern = gemm2_bf16_kernel<EPI, Cfg, PREC>;
   static int granted[kMaxDevices] = {0};
   if (const int rc_attr = ensure_dynamic_smem(kern, Cfg::kSmemBytes, granted)) return rc_attr;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
@@ -696,6 +770,7 @@ int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long l
   p.ln_parts = ln_dim / 128;
   p.stats_out = stats_out;
   p.dbg = g_dbg_buffer;
+  p.out_scale = 1.f;
   // Slot spacing: 21 % of the ideal tile time (K blocks x 4 MMAs x 128 cycles), at most that of a
   // K = 768 tile (1290 cycles: a K = 3072 tile gains nothing from wider slots), plus 5 % between the
   // four lane-quarter warps of a slot.  Measured (tools/gemm_dbg.py, cycles per launch at C2):
@@ -737,6 +812,64 @@ int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long l
   if (residual) return stats_out ? VT_G2_LAUNCH(EPI_RES | EPI_STATS) : VT_G2_LAUNCH(EPI_RES);
   return VT_G2_LAUNCH(0);
 #undef VT_G2_LAUNCH
+}
+
+// FP8 form (behind vt_gemm_fp8 / VT_FP8=1, off the bf16 headline metric): A [M,K] and Bt [N,K] are e4m3 bytes
+// (row strides in bytes, multiples of 16), accumulated in fp32 by tcgen05.mma kind::f8f6f4;
+//   out = act(acc * colscale[n] + bias[n]) (+ residual)      colscale = weight scale of channel n x activation scale
+// out is bf16 [M,N] or, with out_e4m3, e4m3(out * out_scale) (N % 128 == 0, no residual).
+int gemm2_fp8_tcgen05(const void* A, long long lda, const void* Bt, long long ldb, void* out, long long ldo,
+                      int out_e4m3, const float* bias, const float* colscale, const void* residual, long long ldr,
+                      int M, int N, int K, int gelu, float out_scale, int reverse, cudaStream_t stream) {
+  if (!A || !Bt || !out || !colscale || M <= 0 || N <= 0 || K <= 0) return VT_ERR_ARG;
+  if (gelu && residual) return VT_ERR_UNSUPPORTED;
+  if (out_e4m3 && (residual || (N % 128))) return VT_ERR_UNSUPPORTED;
+  if ((K % 16) || (lda % 16) || (ldb % 16) || (N % 8) || (ldo % (out_e4m3 ? 16 : 8)) || (residual && (ldr % 8)))
+    return VT_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bt) | reinterpret_cast<uintptr_t>(out) |
+       reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(bias) |
+       reinterpret_cast<uintptr_t>(colscale)) & 15)
+    return VT_ERR_ALIGN;
+
+  CUtensorMap ta, tb, to, tr;
+  int rc = make_tmap_u8_2d(&ta, A, K, M, lda, 2 * BK, BM, TMAP_SW_128);
+  if (rc) return rc;
+  rc = make_tmap_u8_2d(&tb, Bt, K, N, ldb, 2 * BK, BNH, TMAP_SW_128);
+  if (rc) return rc;
+  if (out_e4m3) rc = make_tmap_u8_2d(&to, out, N, M, ldo, 128, 32, TMAP_SW_128);
+  else rc = make_tmap_bf16_2d(&to, out, N, M, ldo, kChunkCols, 32, TMAP_SW_128);
+  if (rc) return rc;
+  if (residual) {
+    rc = make_tmap_bf16_2d(&tr, residual, N, M, ldr, kChunkCols, 32, TMAP_SW_128);
+    if (rc) return rc;
+  } else {
+    tr = to;
+  }
+
+  Gemm2Params p;
+  p.M = M; p.N = N; p.K = K;
+  p.num_m_tiles = (M + 2 * BM - 1) / (2 * BM);
+  p.num_n_tiles = (N + BN - 1) / BN;
+  p.reverse = reverse;
+  p.bias = bias;
+  p.rowstats = nullptr;
+  p.colsum = colscale;
+  p.ln_inv_dim = 0.f;
+  p.ln_eps = 0.f;
+  p.ln_parts = 0;
+  p.stats_out = nullptr;
+  p.dbg = g_dbg_buffer;
+  p.out_scale = out_scale;
+  long long ideal = static_cast<long long>((K + 2 * BK - 1) / (2 * BK)) * 512;
+  if (ideal > 6144) ideal = 6144;
+  p.pace = static_cast<int>(ideal * 210 / 1000);
+  p.pace_q = static_cast<int>(ideal * 50 / 1000);
+  if (out_e4m3)
+    return gelu ? launch2<EPI_CSCALE | EPI_GELU, G2Deep, 2>(ta, tb, to, tr, p, stream)
+                : launch2<EPI_CSCALE, G2Deep, 2>(ta, tb, to, tr, p, stream);
+  if (residual) return launch2<EPI_CSCALE | EPI_RES, G2Deep, 1>(ta, tb, to, tr, p, stream);
+  if (gelu) return launch2<EPI_CSCALE | EPI_GELU, G2Deep, 1>(ta, tb, to, tr, p, stream);
+  return launch2<EPI_CSCALE, G2Deep, 1>(ta, tb, to, tr, p, stream);
 }
 
 }  // namespace vt

@@ -23,6 +23,10 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_
                       uint64_t row_stride_elems, uint32_t box_cols, uint32_t box_rows,
                       TmapSwizzle sw);
 
+// 2-D tensor of single bytes (e4m3 operands / outputs): `cols` contiguous bytes per row.
+int make_tmap_u8_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows,
+                    uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows, TmapSwizzle sw);
+
 // 3-D bf16 tensor (cols, rows, batch) with element strides for rows and batches.
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows,
                       uint64_t batch, uint64_t row_stride_elems, uint64_t batch_stride_elems,

@@ -16,6 +16,7 @@ _lib: Optional[ctypes.CDLL] = None
 VT_F32 = 0
 VT_BF16 = 1
 VT_U8 = 2     # raw NHWC pixels of vt_patch_embed
+VT_E4M3 = 3   # FP8 path (vt_gemm_fp8 / vt_layernorm_fp8)
 VT_PG_PUT = 1  # vt_pool_cls_allgather modes
 VT_PG_GET = 2
 
@@ -37,6 +38,10 @@ SIGNATURES = {
                         _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i32, _c_f32, _c_ptr, _c_ptr],
     "vt_gemm_strided": [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32,
                         _c_i64p, _c_i64p, _c_i64p, _c_f32, _c_i32, _c_i32, _c_ptr],
+    "vt_gemm_fp8": [_c_ptr, _c_i64, _c_ptr, _c_i64, _c_ptr, _c_i64, _c_i32, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i32,
+                    _c_i32, _c_i32, _c_i32, _c_f32, _c_ptr],
+    "vt_layernorm_fp8": [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i32, _c_i64, _c_i64, _c_f32, _c_f32, _c_ptr],
+    "vt_quantize_rows_fp8": [_c_ptr, _c_i64, _c_ptr, _c_i64, _c_ptr, _c_i32, _c_i32, _c_ptr],
     "vt_bgemm": [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _c_i64p, _c_i64p,
                  _c_i64p, _c_i32, _c_f32, _c_i32, _c_i32, _c_ptr],
     "vt_pack_bf16": [_c_ptr, _c_i32, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i64p, _c_i64p, _c_i32, _c_i32,

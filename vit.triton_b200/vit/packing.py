@@ -126,6 +126,61 @@ def pack_block_folded(block) -> SimpleNamespace:
     return SimpleNamespace(wqkv=wqkv, bqkv=bqkv, cqkv=None, w1=w1, b1=b1, c1=None)
 
 
+# ------------------------------------------------------------------------------------------------ FP8 (optional)
+FP8_ACT_SCALE = 16.0     # LayerNorm outputs are quantised as e4m3(y * 16): |LN(x)| <= sqrt(dim - 1), 448 / 16 = 28
+FP8_MID_SCALE = 8.0      # GELU outputs (fc2's operand) as e4m3(g * 8), saturating at |g| = 56
+
+
+def fp8_supported(x: torch.Tensor, dim: int, mlp_dim: int) -> bool:
+    return x.is_cuda and x.dtype == torch.bfloat16 and dim % 16 == 0 and mlp_dim % 128 == 0
+
+
+def quantize_weight_fp8(w_nk: torch.Tensor) -> tuple:
+    """bf16 [N, K] K-major weight -> (e4m3 bytes [N, K], fp32 per-output-channel scales [N])."""
+    assert w_nk.is_cuda and w_nk.dtype == torch.bfloat16 and w_nk.is_contiguous()
+    N, K = w_nk.shape
+    w8 = torch.empty((N, K), device=w_nk.device, dtype=torch.uint8)
+    scales = torch.empty((N,), device=w_nk.device, dtype=torch.float32)
+    _lib.call("vt_quantize_rows_fp8", w_nk.data_ptr(), K, w8.data_ptr(), K, scales.data_ptr(), N, K,
+              _lib.stream_ptr(w_nk))
+    return w8, scales
+
+
+def pack_block_fp8(block) -> SimpleNamespace:
+    """e4m3 weights of the QKV / fc1 / fc2 layers of one block with their per-channel dequantisation scales,
+    the activation scales already divided out (the GEMM epilogue is acc * colscale + bias)."""
+    att = block.attention.packed()
+    mlp = block.packed()
+    wqkv8, sqkv = quantize_weight_fp8(att.wqkv)
+    w18, s1 = quantize_weight_fp8(mlp.w1)
+    w28, s2 = quantize_weight_fp8(mlp.w2)
+    return SimpleNamespace(wqkv8=wqkv8, cqkv=(sqkv / FP8_ACT_SCALE).contiguous(), w18=w18,
+                           c1=(s1 / FP8_ACT_SCALE).contiguous(), w28=w28, c2=(s2 / FP8_MID_SCALE).contiguous())
+
+
+def layernorm_fp8(x: torch.Tensor, ln, scale: float = FP8_ACT_SCALE) -> torch.Tensor:
+    """(B, N, D) bf16 -> e4m3(LN(x) * scale) as uint8 (B, N, D): LayerNorm with the GEMM operand's quantisation fused."""
+    B, N, D = x.shape
+    out = torch.empty((B, N, D), device=x.device, dtype=torch.uint8)
+    if out.numel():
+        _lib.call("vt_layernorm_fp8", x.data_ptr(), ln.weight.data_ptr(), ln.bias.data_ptr(), out.data_ptr(), B * N, D,
+                  D, D, float(ln.eps), float(scale), _lib.stream_ptr(x))
+    return out
+
+
+def linear_fp8(x8: torch.Tensor, w8: torch.Tensor, colscale: torch.Tensor, bias32: torch.Tensor, gelu: bool = False,
+               residual: Optional[torch.Tensor] = None, out_fp8: bool = False, out_scale: float = 1.0) -> torch.Tensor:
+    """out = act((x8 @ w8^T) * colscale + bias) (+ residual) on tcgen05.mma kind::f8f6f4; x8 / w8 are e4m3 bytes."""
+    B, N, K = x8.shape
+    n_out = w8.shape[0]
+    out = torch.empty((B, N, n_out), device=x8.device, dtype=torch.uint8 if out_fp8 else torch.bfloat16)
+    if out.numel():
+        _lib.call("vt_gemm_fp8", x8.data_ptr(), K, w8.data_ptr(), K, out.data_ptr(), n_out,
+                  _lib.VT_E4M3 if out_fp8 else _lib.VT_BF16, bias32.data_ptr(), colscale.data_ptr(),
+                  _lib.ptr(residual), n_out, B * N, n_out, K, 1 if gelu else 0, float(out_scale), _lib.stream_ptr(x8))
+    return out
+
+
 def pack_embeddings(emb) -> SimpleNamespace:
     w = emb.projection.weight.detach()
     D = w.shape[0]

@@ -19,6 +19,7 @@ Differences from the reference that are deliberate: the p
 width can be set, and dtype / device follow the parameters instead of module-level globals.
 """
 import math
+import os
 from typing import Optional
 
 import torch
@@ -46,6 +47,22 @@ _FUSED = True
 # layernorm_before / both — 24 launches and 3.7 GB of activation traffic less per forward.
 _FOLD_LN = True
 _FOLD_LN_MLP = True    # layernorm_after -> fc1 fold (statistics from the out-proj epilogue), see set_layernorm_folding
+
+
+# Optional FP8 path (off by default and off the bf16 headline metric; VT_FP8=1 or set_fp8(True)):
+# the QKV, fc1 and fc2 GEMMs of every block run on e4m3 operands (tcgen05.mma kind::f8f6f4): the LayerNorms write
+# e4m3 directly, fc1's epilogue writes e4m3 for fc2, weights are quantised per output channel at pack time; the
+# attention, the out-projection, the residual stream and the final LayerNorm stay bf16.
+_FP8 = os.environ.get("VT_FP8", "0") == "1"
+
+
+def set_fp8(enabled: bool) -> None:
+    global _FP8
+    _FP8 = bool(enabled)
+
+
+def fp8_enabled() -> bool:
+    return _FP8
 
 
 def set_fused(enabled: bool) -> None:
@@ -175,6 +192,25 @@ class Transformer(packing.PackedMixin, nn.Module):
     def _build_packed_folded(self):
         return packing.pack_block_folded(self)
 
+    def _packed_sources_fp8(self):
+        return list(self.parameters())
+
+    def _build_packed_fp8(self):
+        return packing.pack_block_fp8(self)
+
+    def forward_fp8(self, x: torch.Tensor) -> torch.Tensor:
+        """Block forward with the QKV / fc1 / fc2 GEMMs on e4m3 operands (7 launches; see the note at _FP8)."""
+        att = self.attention.packed()
+        mlp = self.packed()
+        q8 = self.packed("fp8")
+        x = x.contiguous()
+        qkv = packing.linear_fp8(packing.layernorm_fp8(x, self.layernorm_before), q8.wqkv8, q8.cqkv, att.bqkv)
+        ctx = flash_attention(qkv, self.num_heads, 1.0 / math.sqrt(self.d_out))
+        res = packing.linear(ctx, att.wo, att.bo, residual=x)
+        mid8 = packing.linear_fp8(packing.layernorm_fp8(res, self.layernorm_after), q8.w18, q8.c1, mlp.b1, gelu=True,
+                                  out_fp8=True, out_scale=packing.FP8_MID_SCALE)
+        return packing.linear_fp8(mid8, q8.w28, q8.c2, mlp.b2, residual=res)
+
     def forward_folded(self, x: torch.Tensor, ln1_stats: Optional[torch.Tensor]):
         """Block forward with layernorm_before folded into the QKV GEMM (bf16 only).
 
@@ -220,13 +256,21 @@ class Encoder(nn.Module):
             for _ in range(self.num_layers)
         )
 
+    def fp8_active(self, x) -> bool:
+        return bool(_FUSED and _FP8 and len(self.layer) > 0 and x.numel() > 0 and
+                    packing.fp8_supported(x, self.hidden_dim, self.layer[0].mlp_dim))
+
     def folding_active(self, x) -> bool:
-        return bool(_FUSED and _FOLD_LN and len(self.layer) > 0 and x.numel() > 0 and
+        return bool(_FUSED and _FOLD_LN and not self.fp8_active(x) and len(self.layer) > 0 and x.numel() > 0 and
                     packing.folding_supported(x, self.hidden_dim, self.layer[0].mlp_dim))
 
     def forward(self, x, ln1_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``ln1_stats``: row statistics of x written by the patch-embedding epilogue (see
         ``Embeddings.forward``); without them block 0's layernorm_before runs as a kernel."""
+        if self.fp8_active(x):
+            for layer in self.layer:
+                x = layer.forward_fp8(x)
+            return x
         if self.folding_active(x):
             # layernorm_before folded into the QKV GEMM; row statistics of each block's output are
             # produced by its last GEMM's epilogue
