@@ -360,10 +360,12 @@ class StepRunner:
         return self.launches_per_graph * steps if self.graphs else eager_count
 
 
-def quick_config(name, world, rank, dev, steps=5, warmup=3):
-    """Short device-resident measurement of another BASELINE config on the same box (side field)."""
+def quick_config(name, world, rank, dev, steps=5, warmup=3, fp8=False):
+    """Short device-resident measurement of another BASELINE config on the same box (side field);
+    ``fp8``: with the optional FP8 path (e4m3 QKV / fc1 / fc2 GEMMs) switched on for the measurement."""
     import torch
     from vit import configs
+    from vit import vit as vit_mod
     from vit.parallel import DataParallelVIT
     arch = CONFIGS[name][0]
     batch = per_gpu_batch(name, world)
@@ -374,18 +376,22 @@ def quick_config(name, world, rank, dev, steps=5, warmup=3):
     g = torch.Generator().manual_seed(99 + rank)
     xs = [torch.randn((batch, 3, S, S), generator=g).to(torch.bfloat16).to(dev) for _ in range(2)]
     run = StepRunner(dp, world, batch * world, use_graph=False)
-    with torch.no_grad():
-        for i in range(warmup):
-            run(xs[i & 1])
-        run.finish()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            run(xs[i & 1])
-        run.finish()
-        e1.record()
-        torch.cuda.synchronize()
+    vit_mod.set_fp8(fp8)
+    try:
+        with torch.no_grad():
+            for i in range(warmup):
+                run(xs[i & 1])
+            run.finish()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                run(xs[i & 1])
+            run.finish()
+            e1.record()
+            torch.cuda.synchronize()
+    finally:
+        vit_mod.set_fp8(False)
     ms = e0.elapsed_time(e1) / steps
     del model, dp, xs
     torch.cuda.empty_cache()
@@ -615,6 +621,8 @@ def main():
                 others[name] = quick_config(name, world, rank, dev)
             if world == 1:
                 others["c1"] = c1_fp32_latency(dev)
+                others["c2_fp8"] = quick_config("c2", world, rank, dev, steps=10, fp8=True)
+                others["c2_fp8"]["dtype"] = "e4m3 QKV / fc1 / fc2 operands (VT_FP8=1), NOT the headline bf16 metric"
 
     # ----------------------------------------------------------------- reduce over ranks
     other_ms = [others[k]["ms_per_step"] for k in sorted(others) if "ms_per_step" in others[k]]
