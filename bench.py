@@ -236,6 +236,16 @@ def classify_launch(name, args):
         es = {0: 4, 1: 2, 2: 1}[pix_dtype]
         n = (S // P) ** 2
         return "patch_embed", 2.0 * B * n * C * P * P * D, float(B) * (C * S * S * es + (n + 1) * D * 2) + C * P * P * D * 2
+    if name == "vt_patch_embed_gemm":      # gather + token-mode GEMM, timed as one unit
+        pix_dtype, B, C, S, P, D = args[1], args[9], args[10], args[11], args[12], args[13]
+        es = {0: 4, 1: 2, 2: 1}[pix_dtype]
+        n = (S // P) ** 2
+        return "patch_embed", 2.0 * B * n * C * P * P * D, float(B) * (C * S * S * es + (n + 1) * D * 2) + C * P * P * D * 2
+    if name == "vt_gemm_fp8":
+        M, N, K = args[11], args[12], args[13]
+        return f"gemm_fp8 N={N} K={K}", 2.0 * M * N * K, None
+    if name == "vt_layernorm_fp8":
+        return "layernorm_fp8", None, float(args[4]) * args[5] * 3
     if name == "vt_layernorm":
         rows, dim, in_dt, out_dt = args[4], args[5], args[9], args[10]
         return "layernorm", None, float(rows) * dim * ({0: 4, 1: 2}[in_dt] + {0: 4, 1: 2}[out_dt])
@@ -281,7 +291,11 @@ def roofline_kernels(agg, peaks, tensor_peak, sm_mhz, steps):
         sec = a["ms"] / 1e3
         e = {"kernel": label, "launches_per_step": a["launches"] / steps, "avg_launch_us": a["ms"] * 1e3 / a["launches"],
              "ms_per_step": a["ms"] / steps}
-        if label.startswith("gemm"):
+        if label.startswith("gemm_fp8"):
+            tf = a["flops"] / sec / 1e12
+            e.update(bound="tensor", achieved=tf, peak=2 * tensor_peak, unit="TFLOP/s", frac=tf / (2 * tensor_peak),
+                     peak_note="fp8 dense = 2 x the measured bf16 figure (nominal ratio; no measured fp8 peak on file)")
+        elif label.startswith("gemm"):
             tf = a["flops"] / sec / 1e12
             e.update(bound="tensor", achieved=tf, peak=tensor_peak, unit="TFLOP/s", frac=tf / tensor_peak)
         elif label.startswith("attention"):
@@ -550,8 +564,8 @@ def main():
     ms_total = start.elapsed_time(stop)
     hooked_ms_total = h_start.elapsed_time(h_stop)
     kagg = timer.summary()
-    gemm_ms = sum(v["ms"] for k, v in kagg.items() if k.startswith("gemm"))
-    n_gemm = sum(v["launches"] for k, v in kagg.items() if k.startswith("gemm"))
+    gemm_ms = sum(v["ms"] for k, v in kagg.items() if k.startswith("gemm N"))        # the bf16 dense layers
+    n_gemm = sum(v["launches"] for k, v in kagg.items() if k.startswith("gemm N"))
     kernels_ms = sum(v["ms"] for v in kagg.values())
 
     # ----------------------------------------------------------------- end-to-end from pinned host memory
@@ -698,7 +712,9 @@ def main():
         "metric": "images_per_sec", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak" if CONFIGS[args.config][2] == "per_gpu" or args.batch else "strong",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "vs_baseline": None,
+        "dtype": "bf16" if os.environ.get("VT_FP8", "0") != "1" else "e4m3 QKV/fc1/fc2 operands + bf16 (VT_FP8=1: not the BASELINE metric)",
+        "data": "synthetic",
         "config": {"workload": desc, "arch": arch, "per_gpu_batch": batch, "global_batch": global_batch,
                    "tokens": N_tok, "parallelism": f"dp{world}" if world > 1 else "single",
                    "l2": f"{n_rot} distinct input batches rotated; per-step activation footprint > L2",

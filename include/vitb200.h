@@ -185,6 +185,17 @@ int vt_patch_embed_stats(const void* pixels, int32_t pix_dtype, const void* w, i
                          const float* posb, void* out, int32_t out_dtype, float* stats_out, int32_t B,
                          int32_t C, int32_t S, int32_t P, int32_t D, void* stream);
 
+/* K2 as two launches (the default for bf16 models): a bandwidth-bound gather of the pixels into padded bf16 patch
+ * rows — every pixel read once — followed by the 2-CTA tcgen05 GEMM in token mode, whose epilogue adds the conv bias
+ * and the position table and (stats_out != NULL, D % 128 == 0) writes the row statistics like vt_patch_embed_stats.
+ * pixels / pix_dtype / w / ldw as for vt_patch_embed (ldw >= C*P*P, multiple of 8: the K padding of w must be zero);
+ * bias f32 [D] = conv bias (uint8 pixels: minus the folded mean term); posb bf16 [n+1, D] = position embeddings with
+ * row 0 = cls + pos[0] - bias; out bf16 [B, n+1, D]; workspace: bf16 [B, roundup(n+1, 32), ldw] scratch owned by the
+ * caller (the gathered patch rows).  Same reference entry points replaced as vt_patch_embed. */
+int vt_patch_embed_gemm(const void* pixels, int32_t pix_dtype, const void* w, int64_t ldw, const float* bias,
+                        const void* posb, void* out, float* stats_out, void* workspace, int32_t B, int32_t C, int32_t S,
+                        int32_t P, int32_t D, void* stream);
+
 /* (B,C,H,W) -> (B, (H/P)*(W/P), C*P*P) patch rows in (c,i,j) order.
  * Replaces patching_triton (vit/kernels/patching.py:54-92). */
 int vt_patching(const void* image, void* out, int32_t B, int32_t C, int32_t H, int32_t W, int32_t P,

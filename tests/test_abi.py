@@ -32,7 +32,7 @@ def _lib():
 def test_header_declares_expected_entry_points():
     names = set(_declarations())
     assert {"vt_layernorm", "vt_add", "vt_softmax", "vt_gemm_bf16", "vt_gemm_strided", "vt_flash_attn",
-            "vt_gemm_bf16_ln", "vt_ln_fold", "vt_bgemm", "vt_pack_bf16", "vt_gemm_fp8", "vt_layernorm_fp8", "vt_quantize_rows_fp8", "vt_patch_embed", "vt_patch_embed_stats", "vt_patching", "vt_embed_finalize", "vt_conv2d", "vt_pool_cls", "vt_pool_cls_allgather", "vt_version",
+            "vt_gemm_bf16_ln", "vt_ln_fold", "vt_bgemm", "vt_pack_bf16", "vt_gemm_fp8", "vt_layernorm_fp8", "vt_quantize_rows_fp8", "vt_patch_embed", "vt_patch_embed_stats", "vt_patch_embed_gemm", "vt_patching", "vt_embed_finalize", "vt_conv2d", "vt_pool_cls", "vt_pool_cls_allgather", "vt_version",
             "vt_status_string"} == names
 
 

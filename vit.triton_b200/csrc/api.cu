@@ -39,6 +39,9 @@ int gemm2_fp8_tcgen05(const void*, long long, const void*, long long, void*, lon
 int layernorm_e4m3(const void*, const void*, const void*, void*, long long, int, long long, long long, float, float,
                    cudaStream_t);
 int quantize_rows_e4m3(const void*, long long, void*, long long, float*, int, int, cudaStream_t);
+int patch_gather(const void*, int, void*, int, int, int, int, int, int, cudaStream_t);
+int gemm2_patch_tokens(const void*, long long, const void*, long long, void*, const float*, const void*, float*, int, int,
+                       int, int, int, int, cudaStream_t);
 int ln_fold(const void*, long long, const float*, const float*, const float*, void*, long long, float*, float*, int,
             int, int, cudaStream_t);
 int embed_finalize(void*, const void*, const void*, int, int, int, int, cudaStream_t);
@@ -210,6 +213,21 @@ int vt_patch_embed_stats(const void* pixels, int32_t pix_dtype, const void* w, i
 int vt_ln_fold(const void* w, int64_t ldw, const float* bias, const float* gamma, const float* beta, void* w_out,
                int64_t ldo, float* bias_out, float* colsum_out, int32_t N, int32_t K, int32_t zero_sum, void* stream) {
   return vt::ln_fold(w, ldw, bias, gamma, beta, w_out, ldo, bias_out, colsum_out, N, K, zero_sum, S(stream));
+}
+
+int vt_patch_embed_gemm(const void* pixels, int32_t pix_dtype, const void* w, int64_t ldw, const float* bias,
+                        const void* posb, void* out, float* stats_out, void* workspace, int32_t B, int32_t C, int32_t S_,
+                        int32_t P, int32_t D, void* stream) {
+  if (P <= 0 || S_ <= 0 || (S_ % P) || !workspace) return VT_ERR_ARG;
+  const int n = (S_ / P) * (S_ / P);
+  const int tokens = n + 1;
+  const int tok_pad = (tokens + 31) & ~31;
+  const int K = C * P * P;
+  if (ldw < K || (ldw % 8)) return VT_ERR_ALIGN;
+  const int rc = vt::patch_gather(pixels, pix_dtype, workspace, B, C, S_, P, tok_pad, static_cast<int>(ldw), S(stream));
+  if (rc) return rc;
+  return vt::gemm2_patch_tokens(workspace, ldw, w, ldw, out, bias, posb, stats_out, B, tok_pad, tokens, D,
+                                static_cast<int>(ldw), next_direction(), S(stream));
 }
 
 int vt_patching(const void* image, void* out, int32_t B, int32_t C, int32_t H, int32_t W, int32_t P,

@@ -100,6 +100,11 @@ struct Gemm2Params {
   // 0 = off; pace_q = additional stagger between the four lane-quarter warps of a slot
   int pace, pace_q;
   float out_scale;   // PREC 2: multiplier applied before the e4m3 cast of the output
+  // Token mode (patch embedding, EPI_RES): the M rows are images of tok_pad rows each (tok_pad % 32 == 0, so a
+  // 32-row epilogue tile never straddles two images), of which the first `tokens` are real.  The output map is
+  // 3-D (column, token, image: TMA clips the padding rows), the "residual" map is the [tokens, N] position table
+  // addressed by token, and row statistics go to row image * tokens + token.  0 = off.
+  int tok_pad, tokens;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -424,14 +429,20 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       int row0, col0;
       tile_origin(t, row0, col0);
       const float4 b4 = b4n, c4 = c4n;
+      // token mode: (image, first token) of this warp's 32 rows; res_row = row coordinate of the residual map
+      int img = 0, tok0 = row0;
+      if ((EPI & EPI_RES) && p.tok_pad > 0) {
+        img = row0 / p.tok_pad;
+        tok0 = row0 - img * p.tok_pad;
+      }
 
       if (EPI & EPI_RES) {
         if (lane == 0) {
 #pragma unroll
           for (int c = 0; c < kStageBufs; ++c) {
             mbar_arrive_expect_tx(res_bar(ew, c), kStagingBytes);
-            tma_load_2d(&tma_res, res_bar(ew, c), stage_buf[c], col0 + c * kChunkCols, row0,
-                        kEvictFirst);
+            tma_load_2d(&tma_res, res_bar(ew, c), stage_buf[c], col0 + c * kChunkCols, tok0,
+                        p.tok_pad > 0 ? kEvictNormal : kEvictFirst);
           }
         }
       }
@@ -515,7 +526,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             tma_store_wait_read<0>();
             if (EPI & EPI_RES) {
               mbar_arrive_expect_tx(res_bar(ew, c), kStagingBytes);
-              tma_load_2d(&tma_res, res_bar(ew, c), stage_buf[c], col, row0, kEvictFirst);
+              tma_load_2d(&tma_res, res_bar(ew, c), stage_buf[c], col, tok0, p.tok_pad > 0 ? kEvictNormal : kEvictFirst);
             }
           }
           __syncwarp();
@@ -639,10 +650,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           }
         }
         if ((EPI & EPI_STATS) && c == kChunks - 1) {
-          const int row = row0 + lane;
-          if (col0 < p.N && row < p.M) {          // N % 128 == 0: a warp's two chunks are both in or both out
-            float2* dst = reinterpret_cast<float2*>(p.stats_out) +
-                          static_cast<long long>(row) * (p.N >> 7) + (col0 >> 7);
+          long long row = row0 + lane;
+          bool row_ok = row < p.M;
+          if (p.tok_pad > 0) {
+            row_ok = tok0 + lane < p.tokens;
+            row = static_cast<long long>(img) * p.tokens + tok0 + lane;
+          }
+          if (col0 < p.N && row_ok) {             // N % 128 == 0: a warp's two chunks are both in or both out
+            float2* dst = reinterpret_cast<float2*>(p.stats_out) + row * (p.N >> 7) + (col0 >> 7);
             const float s_sh = st_sum2.x + st_sum2.y, q_sh = st_sq2.x + st_sq2.y;
             *dst = make_float2(fmaf(-128.0f, st_npiv2.x, s_sh), fmaxf(fmaf(-s_sh * (1.0f / 128.0f), s_sh, q_sh), 0.f));
           }
@@ -660,7 +675,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tma_out, stage_buf[c], col, row0);
+            if ((EPI & EPI_RES) && p.tok_pad > 0) tma_store_3d(&tma_out, stage_buf[c], col, tok0, img);
+            else tma_store_2d(&tma_out, stage_buf[c], col, row0);
             tma_store_commit();
           }
         }
@@ -771,6 +787,8 @@ int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long l
   p.stats_out = stats_out;
   p.dbg = g_dbg_buffer;
   p.out_scale = 1.f;
+  p.tok_pad = 0;
+  p.tokens = 0;
   // Slot spacing: 21 % of the ideal tile time (K blocks x 4 MMAs x 128 cycles), at most that of a
   // K = 768 tile (1290 cycles: a K = 3072 tile gains nothing from wider slots), plus 5 % between the
   // four lane-quarter warps of a slot.  Measured (tools/gemm_dbg.py, cycles per launch at C2):
@@ -812,6 +830,58 @@ int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long l
   if (residual) return stats_out ? VT_G2_LAUNCH(EPI_RES | EPI_STATS) : VT_G2_LAUNCH(EPI_RES);
   return VT_G2_LAUNCH(0);
 #undef VT_G2_LAUNCH
+}
+
+// K2b: the patch-embedding GEMM in token mode.  A = gathered patch rows [B * tok_pad, K] (patch_gather.cu: row 0 of
+// every image and the rows >= tokens are zero), W = conv weight [D, K] K-major, bias = conv bias (fp32),
+// posb = bf16 [tokens, D] position table with row 0 = cls + pos[0] - bias:
+//   out[b, t, :] = A[b, t, :] . W^T + bias + posb[t, :]        (t < tokens; + row statistics for the LayerNorm fold)
+int gemm2_patch_tokens(const void* A, long long lda, const void* W, long long ldw, void* out, const float* bias,
+                       const void* posb, float* stats_out, int B, int tok_pad, int tokens, int D, int K, int reverse,
+                       cudaStream_t stream) {
+  if (!A || !W || !out || !bias || !posb || B <= 0 || tokens <= 0 || D <= 0 || K <= 0) return VT_ERR_ARG;
+  if ((tok_pad % 32) || tok_pad < tokens) return VT_ERR_ARG;
+  if ((K % 8) || (lda % 8) || (ldw % 8) || (D % 8)) return VT_ERR_ALIGN;
+  if (stats_out && (D % 128)) return VT_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(out) |
+       reinterpret_cast<uintptr_t>(posb) | reinterpret_cast<uintptr_t>(bias)) & 15)
+    return VT_ERR_ALIGN;
+  if (reinterpret_cast<uintptr_t>(stats_out) & 7) return VT_ERR_ALIGN;
+  const long long M = static_cast<long long>(B) * tok_pad;
+  if (M >= (1LL << 31)) return VT_ERR_UNSUPPORTED;
+
+  CUtensorMap ta, tb, to, tr;
+  int rc = make_tmap_bf16_2d(&ta, A, K, M, lda, BK, BM, TMAP_SW_128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tb, W, K, D, ldw, BK, BNH, TMAP_SW_128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&to, out, D, tokens, B, D, static_cast<uint64_t>(tokens) * D, kChunkCols, 32, TMAP_SW_128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tr, posb, D, tokens, D, kChunkCols, 32, TMAP_SW_128);
+  if (rc) return rc;
+
+  Gemm2Params p;
+  p.M = static_cast<int>(M); p.N = D; p.K = K;
+  p.num_m_tiles = static_cast<int>((M + 2 * BM - 1) / (2 * BM));
+  p.num_n_tiles = (D + BN - 1) / BN;
+  p.reverse = reverse;
+  p.bias = bias;
+  p.rowstats = nullptr;
+  p.colsum = nullptr;
+  p.ln_inv_dim = 0.f;
+  p.ln_eps = 0.f;
+  p.ln_parts = 0;
+  p.stats_out = stats_out;
+  p.dbg = g_dbg_buffer;
+  p.out_scale = 1.f;
+  p.tok_pad = tok_pad;
+  p.tokens = tokens;
+  long long ideal = static_cast<long long>((K + BK - 1) / BK) * 512;
+  if (ideal > 6144) ideal = 6144;
+  p.pace = static_cast<int>(ideal * 210 / 1000);
+  p.pace_q = static_cast<int>(ideal * 50 / 1000);
+  return stats_out ? launch2<EPI_RES | EPI_STATS, G2Wide>(ta, tb, to, tr, p, stream)
+                   : launch2<EPI_RES, G2Wide>(ta, tb, to, tr, p, stream);
 }
 
 // FP8 form (behind vt_gemm_fp8 / VT_FP8=1, off the bf16 headline metric): A [M,K] and Bt [N,K] are e4m3 bytes
@@ -860,6 +930,8 @@ int gemm2_fp8_tcgen05(const void* A, long long lda, const void* Bt, long long ld
   p.stats_out = nullptr;
   p.dbg = g_dbg_buffer;
   p.out_scale = out_scale;
+  p.tok_pad = 0;
+  p.tokens = 0;
   long long ideal = static_cast<long long>((K + 2 * BK - 1) / (2 * BK)) * 512;
   if (ideal > 6144) ideal = 6144;
   p.pace = static_cast<int>(ideal * 210 / 1000);

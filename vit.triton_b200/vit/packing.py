@@ -181,6 +181,14 @@ def linear_fp8(x8: torch.Tensor, w8: torch.Tensor, colscale: torch.Tensor, bias3
     return out
 
 
+def _posb16(pos32: torch.Tensor, cls_token: torch.Tensor, bias32: torch.Tensor) -> torch.Tensor:
+    """bf16 [N, D] position table of the two-launch patch embedding (``vt_patch_embed_gemm``): the GEMM adds the
+    conv bias to EVERY row, so row 0 (CLS: a zero patch row) carries cls + pos[0] - bias."""
+    t = pos32.clone()
+    t[0] += cls_token.detach().float().reshape(-1) - bias32
+    return t.to(torch.bfloat16).contiguous()
+
+
 def pack_embeddings(emb) -> SimpleNamespace:
     w = emb.projection.weight.detach()
     D = w.shape[0]
@@ -192,8 +200,9 @@ def pack_embeddings(emb) -> SimpleNamespace:
     posb = pos.clone()
     posb[0] += emb.cls_token.detach().float().reshape(-1)
     posb[1:] += emb.projection.bias.detach().float()
-    return SimpleNamespace(w=w2d, ldw=kpad, K=K, posb=posb.contiguous(),
-                           bias32=emb.projection.bias.detach().float().contiguous())
+    bias32 = emb.projection.bias.detach().float().contiguous()
+    return SimpleNamespace(w=w2d, ldw=kpad, K=K, posb=posb.contiguous(), bias32=bias32,
+                           posb16=_posb16(pos, emb.cls_token, bias32))
 
 
 def pack_embeddings_u8(emb, image_mean, image_std, rescale_factor: float) -> SimpleNamespace:
@@ -220,7 +229,9 @@ def pack_embeddings_u8(emb, image_mean, image_std, rescale_factor: float) -> Sim
     posb = pos.clone()
     posb[0] += emb.cls_token.detach().float().reshape(-1)
     posb[1:] += emb.projection.bias.detach().float() - offset
-    return SimpleNamespace(w=w2d, ldw=kpad, K=K, posb=posb.contiguous())
+    bias32 = (emb.projection.bias.detach().float() - offset).contiguous()
+    return SimpleNamespace(w=w2d, ldw=kpad, K=K, posb=posb.contiguous(), bias32=bias32,
+                           posb16=_posb16(pos, emb.cls_token, bias32))
 
 
 def patch_embed_u8(emb, x: torch.Tensor, image_mean, image_std, rescale_factor: float,
@@ -254,9 +265,8 @@ def patch_embed_u8(emb, x: torch.Tensor, image_mean, image_std, rescale_factor: 
     step = 65535 * 128 // emb.num_patches
     for b0 in range(0, B, step):
         nb = min(step, B - b0)
-        _embed_call(stats, b0, n_tok, emb.hidden_dim, x[b0:].data_ptr(), _lib.VT_U8, pk.w.data_ptr(), pk.ldw,
-                    pk.posb.data_ptr(), out[b0:].data_ptr(), _lib.VT_BF16, nb, C, S, emb.patch_size,
-                    emb.hidden_dim, stream)
+        _embed_call(stats, b0, n_tok, emb.hidden_dim, pk, x[b0:].data_ptr(), _lib.VT_U8, out[b0:].data_ptr(), nb, C, S,
+                    emb.patch_size, stream, x.device)
     return out
 
 
@@ -359,13 +369,27 @@ def split_weight(w_nk: torch.Tensor, pieces: int) -> torch.Tensor:
     return value
 
 
-def _embed_call(stats, b0, n_tok, dim, *args):
-    """vt_patch_embed, or vt_patch_embed_stats writing the row statistics of images b0.. into ``stats``."""
-    if stats is None:
-        _lib.call("vt_patch_embed", *args)
+def _two_launch_embed() -> bool:
+    """Gather + token-mode GEMM (default) or round 1's single kernel (VT_PATCH_EMBED=1, A/B measurements)."""
+    return os.environ.get("VT_PATCH_EMBED", "2") != "1"
+
+
+def _embed_call(stats, b0, n_tok, dim, pk, pixels_ptr, pix_code, out_ptr, nb, C, S, P, stream, device):
+    """Patch embedding of images b0 .. b0 + nb: ``vt_patch_embed_gemm`` (gather + 2-CTA GEMM in token mode), or the
+    single-kernel ``vt_patch_embed[_stats]``; row statistics of those images go into ``stats`` when given."""
+    s_ptr = None if stats is None else stats.data_ptr() + b0 * n_tok * (dim // STATS_COLS) * 2 * 4
+    if _two_launch_embed():
+        tok_pad = (n_tok + 31) // 32 * 32
+        work = torch.empty((nb, tok_pad, pk.ldw), device=device, dtype=torch.bfloat16)
+        _lib.call("vt_patch_embed_gemm", pixels_ptr, pix_code, pk.w.data_ptr(), pk.ldw, pk.bias32.data_ptr(),
+                  pk.posb16.data_ptr(), out_ptr, s_ptr, work.data_ptr(), nb, C, S, P, dim, stream)
         return
-    s_ptr = stats.data_ptr() + b0 * n_tok * (dim // STATS_COLS) * 2 * 4
-    _lib.call("vt_patch_embed_stats", *args[:7], s_ptr, *args[7:])
+    if stats is None:
+        _lib.call("vt_patch_embed", pixels_ptr, pix_code, pk.w.data_ptr(), pk.ldw, pk.posb.data_ptr(), out_ptr,
+                  _lib.VT_BF16, nb, C, S, P, dim, stream)
+    else:
+        _lib.call("vt_patch_embed_stats", pixels_ptr, pix_code, pk.w.data_ptr(), pk.ldw, pk.posb.data_ptr(), out_ptr,
+                  _lib.VT_BF16, s_ptr, nb, C, S, P, dim, stream)
 
 
 def patch_embed(emb, x: torch.Tensor, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -388,8 +412,8 @@ def patch_embed(emb, x: torch.Tensor, stats: Optional[torch.Tensor] = None) -> t
         step = 65535 * 128 // emb.num_patches
         for b0 in range(0, B, step):
             nb = min(step, B - b0)
-            _embed_call(stats, b0, n_tok, D, x[b0:].data_ptr(), _lib.dtype_code(x), pk.w.data_ptr(), pk.ldw,
-                        pk.posb.data_ptr(), out[b0:].data_ptr(), _lib.VT_BF16, nb, C, S, P, D, stream)
+            _embed_call(stats, b0, n_tok, D, pk, x[b0:].data_ptr(), _lib.dtype_code(x), out[b0:].data_ptr(), nb, C, S, P,
+                        stream, x.device)
         return out
     assert stats is None, "Row statistics come out of the bf16 tensor-core patch embedding only"
 
