@@ -106,7 +106,8 @@ def test_matmul_fp32_strided_input():
     a = torch.randn(3, 40, 24, device=dev()).transpose(1, 2)       # (3, 24, 40), non-contiguous
     b = torch.randn(64, 40, device=dev()).t()                       # (40, 64), non-contiguous
     got = matmul(a, b)
-    assert (got - a @ b).abs().max().item() <= 1e-4
+    # fp32 on the tensor cores: 3-piece bf16 split, ~2^-16 per product (values here reach +-25)
+    assert (got.double() - a.double() @ b.double()).abs().max().item() <= 5e-4
 
 
 GEMM_SHAPES = [
@@ -256,7 +257,7 @@ def test_bgemm_rejects_misaligned():
         bg.bgemm(a.data_ptr(), a.data_ptr(), out, out.data_ptr(), 4, 4, 12, 1, 1, (0, 0, 12), (0, 0, 12), (0, 0, 4))
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 3e-2)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
 @pytest.mark.parametrize("shape", [((4, 197, 64), (4, 64, 197)), ((4, 197, 197), (4, 197, 64)), ((2, 50, 128), (2, 128, 256))])
 def test_matmul3_reference_shapes_on_tensor_cores(dtype, tol, shape):
     """matmul3 on the reference's own call shapes (vit/vit.py:66-72: q k^T with 197 keys, P v) — odd row

@@ -653,7 +653,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           long long row = row0 + lane;
           bool row_ok = row < p.M;
           if (p.tok_pad > 0) {
-            row_ok = tok0 + lane < p.tokens;
+            row_ok = row_ok && (tok0 + lane < p.tokens);   // rows past the last image exist in the last tile
             row = static_cast<long long>(img) * p.tokens + tok0 + lane;
           }
           if (col0 < p.N && row_ok) {             // N % 128 == 0: a warp's two chunks are both in or both out
