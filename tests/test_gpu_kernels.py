@@ -358,6 +358,49 @@ def test_flash_attention_two_group_kernel_single_block(B, H, N, gain):
     assert torch.equal(sub, got[:1])
 
 
+@pytest.mark.parametrize("B,H,N", [(3, 6, 197), (2, 4, 100), (40, 12, 197)])
+def test_flash_attention_bounded_logit_path_vs_exact_path(B, H, N):
+    """attn5 skips the row-max pass for (image, head) items whose logits are bounded by |q||k| (Cauchy-Schwarz,
+    csrc/attn5_sm100.cu kLogitBound5) and keeps the exact two-pass softmax for the others.  Heads with gains
+    0.5 ... 8 put both kinds of item (and the threshold region, gain 2) into ONE launch, alternating inside a CTA;
+    softmax is shift-invariant, so the two paths must agree to rounding — and with the fp32 reference."""
+    import ctypes
+    from vit.kernels import _lib, flash_attention
+    lib = _lib.load()
+    lib.vt_debug_set_attn_bound.argtypes = [ctypes.c_int]
+    lib.vt_debug_set_attn_bound.restype = None
+    gains = torch.tensor([0.5, 8.0, 1.0, 2.0, 4.0, 1.5, 2.2, 0.1, 3.0, 1.0, 6.0, 2.0], device=dev())[:H]
+    qkv = torch.randn(B, N, 3, H, 64, device=dev())
+    qkv[:, :, :2] *= gains.view(1, 1, 1, H, 1)
+    qkv[B // 2, :, 0, 0] *= 30.0          # one image whose first head is far over the bound
+    qkv = qkv.view(B, N, 3 * H * 64).bfloat16()
+    want = _attn_ref(qkv, H)
+    try:
+        lib.vt_debug_set_attn_bound(1)
+        fast = flash_attention(qkv, H)
+        lib.vt_debug_set_attn_bound(0)
+        exact = flash_attention(qkv, H)
+    finally:
+        lib.vt_debug_set_attn_bound(-1)
+    assert torch.isfinite(fast.float()).all() and torch.isfinite(exact.float()).all()
+    assert rel_err(exact, want) <= 2e-2
+    assert rel_err(fast, want) <= 2e-2
+    # path against path: one bf16 rounding of P and of the output apart
+    assert (fast.float() - exact.float()).abs().max().item() <= 3e-2
+    assert rel_err(fast, exact) <= 1e-2
+
+
+def test_flash_attention_bounded_logit_path_zero_and_constant_rows():
+    """All-zero q / k (every logit 0) and constant keys: the unshifted exponentials are exactly 1."""
+    from vit.kernels import flash_attention
+    qkv = torch.randn(2, 197, 3, 2, 64, device=dev())
+    qkv[0, :, 0] = 0.0
+    qkv[1, :, 1] = 0.25
+    qkv = qkv.view(2, 197, 3 * 2 * 64).bfloat16()
+    got = flash_attention(qkv, 2)
+    assert rel_err(got, _attn_ref(qkv, 2)) <= 1e-2
+
+
 def test_flash_attention_peaky_scores():
     """Large logits: the online max subtraction must keep exp() in range."""
     from vit.kernels import flash_attention

@@ -32,11 +32,11 @@ for (B, H, N, dh) in shapes:
     print(f"B={B} H={H} N={N} dh={dh}: {us:.1f} us/launch (20 back-to-back)")
     d = dbg[:2 * 148 * 8].view(148, 2, 8).double()
     n = B * H * nq / 296
-    names = ["wait-S", "row max", "exchange", "exp", "wait-turn", "-", "-"]
+    names = ["wait-S", "row max", "exchange", "exp", "wait-turn", "norm bound", "-"]
     for g in range(2):
         print(f"   group {g} per item cycles: " + ", ".join(f"{nm} {d[:, g, i].mean()/n:.0f}" for i, nm in enumerate(names))
               + f", total {d[:, g, 7].mean()/n:.0f}")
     m = dbg[2 * 148 * 8:].view(148, 8).double()
     ni = B * H * nq / 148
     print("   MMA issuer per item cycles: " + ", ".join(f"{nm} {m[:, i].mean()/ni:.0f}" for i, nm in
-                                                       enumerate(["wait-V", "wait-O-read", "wait-P", "issue PV + S"])))
+                                                       enumerate(["wait-V", "wait-O-read", "wait-P", "issue PV", "wait Q/K", "issue S"])))

@@ -7,7 +7,7 @@ from vit.kernels import _lib
 lib = _lib.load()
 lib.vt_debug_set_buffer.argtypes = [ctypes.c_void_p]
 lib.vt_debug_set_buffer.restype = None
-M = 256 * 197
+M = int(os.environ.get("VT_DBG_M", 256 * 197))
 dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
 CASES = ((768, 2304, 0, False, ""), (768, 2304, 0, False, "lnf"), (768, 2304, 0, False, "lnz"), (768, 3072, 1, False, ""),
          (768, 3072, 1, False, "lnf"), (768, 3072, 1, False, "lnz"),

@@ -1,0 +1,55 @@
+"""In-kernel cycle accounting of the GEMM launches INSIDE a C2 forward (developer tool): the same counters as
+tools/gemm_dbg.py, but taken while the model runs (cold operands, the power-capped clock of the real step)."""
+import collections, ctypes, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "vit.triton_b200"))
+import torch
+from vit import configs
+from vit.vit import VIT
+from vit.kernels import _lib
+lib = _lib.load()
+lib.vt_debug_set_buffer.argtypes = [ctypes.c_void_p]
+lib.vt_debug_set_buffer.restype = None
+arch = sys.argv[1] if len(sys.argv) > 1 else "vit-b16-224"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+m = VIT(**configs.vit_kwargs(arch)).to("cuda", torch.bfloat16)
+with torch.no_grad():
+    for p_ in m.parameters():
+        p_.copy_(torch.randn_like(p_) * 0.02)
+S = configs.ARCHS[arch]["image_size"]
+x = torch.randn(B, 3, S, S, device="cuda").bfloat16()
+bufs = []
+def hook(name, before, args=None):
+    if name not in ("vt_gemm_bf16_ln", "vt_gemm_bf16"):
+        return
+    if before:
+        b = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+        if name == "vt_gemm_bf16_ln":
+            M, N, K, gelu, res = args[9], args[10], args[11], args[12], args[7]
+        else:
+            M, N, K, gelu, res = args[10], args[11], args[12], args[13], args[8]
+        bufs.append(((M, N, K, int(gelu), res is not None), b))
+        lib.vt_debug_set_buffer(b.data_ptr())
+    else:
+        lib.vt_debug_set_buffer(None)
+with torch.no_grad():
+    for _ in range(30):
+        m(x)
+    torch.cuda.synchronize()
+    _lib.event_hook = hook
+    for _ in range(3):
+        m(x)
+    _lib.event_hook = None
+    torch.cuda.synchronize()
+agg = collections.OrderedDict()
+for key, b in bufs:
+    agg.setdefault(key, []).append(b.view(148, 8).double())
+for (M, N, K, gelu, res), ds in agg.items():
+    d = torch.stack(ds).mean(0)
+    tiles = -(-M // 256) * -(-N // 256)
+    per = tiles / 74
+    lead = d[0::2]
+    print(f"M={M} N={N} K={K} gelu={gelu} res={res} x{len(ds)}: tiles/cluster {per:.1f}; total cyc {d[:,5].mean():.0f} (max {d[:,5].max():.0f}); per tile: "
+          f"epi wait-tfull {d[:,0].mean()/per:.0f}, epi busy {d[:,1].mean()/per:.0f}, store-drain {d[:,6].mean()/per:.0f}, "
+          f"mma wait-full {lead[:,2].mean()/per:.0f}, mma wait-tempty {lead[:,3].mean()/per:.0f}, prod wait-empty {d[:,4].mean()/per:.0f}, "
+          f"period {d[:,5].mean()/per:.0f}")

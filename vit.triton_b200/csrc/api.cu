@@ -21,6 +21,7 @@ int gemm2_bf16_tcgen05(const void*, long long, const void*, long long, void*, lo
                        float*, int, cudaStream_t);
 void gemm2_set_debug_buffer(void*);
 void attn5_set_debug_buffer(void*);
+void attn5_set_bound(int);
 int simt_gemm(const void*, const void*, void*, const void*, int, int, int, int, int,
               const long long*, const long long*, const long long*, float, int, int, cudaStream_t);
 int attn5_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
@@ -77,6 +78,9 @@ void vt_debug_set_buffer(void* ptr) { vt::gemm2_set_debug_buffer(ptr); }
 void vt_debug_set_attn_buffer(void* ptr) {
   vt::attn5_set_debug_buffer(ptr);
 }
+// Developer hook: 0 = every attention item takes the exact two-pass softmax, 1 = items whose logits are bounded
+// skip the row-max pass (the default), -1 = back to the VT_ATTN_NO_BOUND environment default.
+void vt_debug_set_attn_bound(int mode) { vt::attn5_set_bound(mode); }
 
 const char* vt_status_string(int status) {
   switch (status) {

@@ -35,6 +35,8 @@
 //                     a group's period is wait-S + max + exp and the kernel runs against the MUFU pipe.
 //
 // Sequences longer than 208 keys and head dim 80 run attn5mb_fwd_kernel below (online softmax over KV blocks).
+#include <cstdlib>
+
 #include "attn_softmax.cuh"
 #include "common.cuh"
 #include "tensormap.h"
@@ -71,6 +73,7 @@ struct Attn5Params {
   int bkv;            // key rows loaded per item (N rounded up to 16)
   long long total_items;
   int reverse;        // walk the images from the last to the first (L2 reuse, see api.cu)
+  int no_bound;       // 1: every item takes the exact two-pass softmax (VT_ATTN_NO_BOUND=1, A/B and tests)
   float scale_log2;
   long long* dbg;     // cycle counters, developer build only (make EXTRA=-DVT_ATTN5_DBG, tools/attn_dbg.py)
 };
@@ -189,6 +192,32 @@ __device__ __forceinline__ void exp_groups5(uint32_t a, int nv, float scale_log2
   tmem_st_wait();
 }
 
+// |row|^2 of one 64-element bf16 row (128 B) of a SWIZZLE_128B tile, packed bf16x2 FMAs on four chains (the
+// result only feeds a bound with a 10 % margin).  Chunk order is rotated by the row's swizzle phase so that
+// the 32 lanes of a warp (32 consecutive rows) spread over all banks.
+__device__ __forceinline__ float row_sumsq_bf16x64(uint32_t row_addr, int sw) {
+  uint32_t acc[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint32_t x[4];
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3])
+                 : "r"(row_addr + (static_cast<uint32_t>(j ^ sw) << 4)));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) asm("fma.rn.bf16x2 %0, %1, %1, %0;" : "+r"(acc[i]) : "r"(x[i]));
+  }
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) t += bf16_lo(acc[i]) + bf16_hi(acc[i]);
+  return t;
+}
+
+// Logits bounded by Cauchy-Schwarz: |scale_log2 * q.k| <= kLogitBound5 for every (query, key) of the item means
+// exp2 needs no shift (softmax is shift-invariant; fp32 / bf16 hold 2^+-64 with room for the row sum and P.V),
+// so the row-max pass and the exchange between the two column halves are skipped (see the softmax warps).
+constexpr float kLogitBound5 = 64.0f;
+constexpr float kBoundMargin5 = 1.21f;     // (1.1)^2 on the squared norms: bf16 accumulation of the sums of squares
+
 __global__ void __launch_bounds__(kThreads5s, 1)
 attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                  const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_o,
@@ -213,6 +242,7 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + slot_off);
   int4* ring = reinterpret_cast<int4*>(smem_gen + slot_off + 8);                 // [kRing5] (16-byte aligned)
   float* xm = reinterpret_cast<float*>(smem_gen + slot_off + 8 + 16 * kRing5);   // [2 groups][2 halves][128]
+  uint32_t* nrm = reinterpret_cast<uint32_t*>(xm + 2 * 2 * kQTile5);             // [2 groups][2 items][q | k][8 warps]
   auto bar = [&](int i) { return bar_base + 8u * i; };
 
   const int warp_idx = threadIdx.x >> 5;
@@ -222,6 +252,10 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     for (int i = 0; i < C_NBARS; ++i)
       mbar_init(bar(i), (i == C_PFULL || i == C_PFULL + 1 || i == C_PHALF || i == C_PHALF + 1 || i == C_XTOK ||
                          i == C_XTOK + 1)       ? 8
+                        : (i == C_QEMPTY || i == C_QEMPTY + 1)
+                            ? 9     // tcgen05.commit of Q K^T + the 8 softmax warps of the group (norm reads)
+                        : (i == C_KEMPTY || i == C_KEMPTY + 1) ? 9 * p.nqt     // the same from every item of the pair
+                        : (i == C_VEMPTY || i == C_VEMPTY + 1) ? p.nqt         // tcgen05.commit of P V of every item
                         : (i == C_OREAD) ? 4
                                          : 1);
     fence_barrier_init();
@@ -247,11 +281,20 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   const uint32_t tmem_base = *tmem_slot_gen;
 
   // Work list of this CTA: items blockIdx.x, blockIdx.x + grid, ...
-  const long long first_item = blockIdx.x;
-  const long long item_step = gridDim.x;
-  const int n_items = (p.total_items > first_item)
-                          ? static_cast<int>((p.total_items - first_item + item_step - 1) / item_step)
+  // Work list of this CTA: (image, head) pairs blockIdx.x, blockIdx.x + grid, ...; a pair is nqt (1 or 2) items,
+  // its query tiles, which follow each other in the item sequence and SHARE one K and one V tile: item `it`
+  // uses Q buffer / score buffer / softmax group it & 1 and K/V stage (it >> kv_shift) & 1.  (Round 2 first loaded
+  // K and V per item: twice the operand traffic, and with two stages per operand the in-order producer could
+  // request an item's K only ~1.3 item periods ahead — the MMA issuer waited 500 cycles per item for Q/K and
+  // 190 for V.  A shared stage is requested three periods ahead.)
+  const long long total_pairs = p.total_items / p.nqt;
+  const long long first_pair = blockIdx.x;
+  const long long pair_step = gridDim.x;
+  const int n_pairs = (total_pairs > first_pair)
+                          ? static_cast<int>((total_pairs - first_pair + pair_step - 1) / pair_step)
                           : 0;
+  const int kv_shift = p.nqt == 2 ? 1 : 0;
+  const int n_items = n_pairs << kv_shift;
   const int nj = (p.N + 15) & ~15;     // score columns (MMA N)
   const int n16 = nj >> 4;             // 16-column groups: half 0 takes the first (n16 + 1) / 2
   const int ng0 = (n16 + 1) >> 1;
@@ -259,14 +302,16 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   if (warp_idx == 16) {
     // ------------------------------------------------------------------ TMA producer
     for (int it = 0; it < n_items; ++it) {
-      const unsigned item = static_cast<unsigned>(first_item + static_cast<long long>(it) * item_step);
-      const int qt = static_cast<int>(item % static_cast<unsigned>(p.nqt));   // total_items < 2^31 (host)
-      const unsigned bh = item / static_cast<unsigned>(p.nqt);
+      const int kvi = it >> kv_shift;                       // K/V stage use counter = local pair index
+      const int qt = it & (p.nqt - 1);
+      const unsigned bh = static_cast<unsigned>(first_pair + static_cast<long long>(kvi) * pair_step);
       const int head = static_cast<int>(bh % static_cast<unsigned>(p.H));
       int img = static_cast<int>(bh / static_cast<unsigned>(p.H));
       if (p.reverse) img = p.B - 1 - img;
       const int b = it & 1;
       const uint32_t ph = (static_cast<uint32_t>(it) >> 1) & 1u;
+      const int s = kvi & 1;
+      const uint32_t kph = (static_cast<uint32_t>(kvi) >> 1) & 1u;
       mbar_wait(bar(C_QEMPTY + b), ph ^ 1u);
       if (elect_one_sync()) {
         // item coordinates for the softmax warps: visible to them through the barrier chain
@@ -276,38 +321,53 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         tma_load_3d(&tma_q, bar(C_QFULL + b), q_smem + b * kQBytes5, head * kDH5, qt * kQTile5, img, kEvictFirst);
       }
       __syncwarp();
-      mbar_wait(bar(C_KEMPTY + b), ph ^ 1u);
-      if (elect_one_sync()) {
-        mbar_arrive_expect_tx(bar(C_KFULL + b), kv_bytes);
-        tma_load_3d(&tma_k, bar(C_KFULL + b), k_smem + b * kv_bytes, head * kDH5, 0, img, kEvictNormal);
+      if (qt == 0) {              // first item of the pair: its K tile
+        mbar_wait(bar(C_KEMPTY + s), kph ^ 1u);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(bar(C_KFULL + s), kv_bytes);
+          tma_load_3d(&tma_k, bar(C_KFULL + s), k_smem + s * kv_bytes, head * kDH5, 0, img, kEvictFirst);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      mbar_wait(bar(C_VEMPTY + b), ph ^ 1u);
-      if (elect_one_sync()) {
-        mbar_arrive_expect_tx(bar(C_VFULL + b), kv_bytes);
-        tma_load_3d(&tma_v, bar(C_VFULL + b), v_smem + b * kv_bytes, head * kDH5, 0, img, kEvictNormal);
+      if (qt == p.nqt - 1) {      // last item of the pair: its V tile (behind the pair's query tiles)
+        mbar_wait(bar(C_VEMPTY + s), kph ^ 1u);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(bar(C_VFULL + s), kv_bytes);
+          tma_load_3d(&tma_v, bar(C_VFULL + s), v_smem + s * kv_bytes, head * kDH5, 0, img, kEvictFirst);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp_idx == 17) {
     // ------------------------------------------------------------------ MMA issuer
     // S_v = Q K^T into score buffer v & 1 (free: PV_{v-2}, issued earlier by this thread, is the last
     // reader of that buffer and tcgen05.mma executes in issue order).
+#ifdef VT_ATTN5_DBG
+    unsigned macc[6] = {0, 0, 0, 0, 0, 0};
+    unsigned mt = static_cast<unsigned>(clock());
+#define VT_MTICK(i) { const unsigned t_ = static_cast<unsigned>(clock()); macc[i] += t_ - mt; mt = t_; }
+#else
+#define VT_MTICK(i)
+#endif
     auto issue_scores = [&](int v) {
       const int b = v & 1;
       const uint32_t ph = (static_cast<uint32_t>(v) >> 1) & 1u;
+      const int kvi = v >> kv_shift;
+      const int s = kvi & 1;
+      VT_MTICK(3)
       mbar_wait(bar(C_QFULL + b), ph);
-      mbar_wait(bar(C_KFULL + b), ph);
+      mbar_wait(bar(C_KFULL + s), (static_cast<uint32_t>(kvi) >> 1) & 1u);
+      VT_MTICK(4)
       tc_fence_after();
       if (elect_one_sync()) {
         const uint32_t idesc = make_idesc_bf16(kQTile5, nj, 0, 0);
         const uint64_t qd = make_desc_kmajor_sw128(q_smem + b * kQBytes5);
-        const uint64_t kd = make_desc_kmajor_sw128(k_smem + b * kv_bytes);
+        const uint64_t kd = make_desc_kmajor_sw128(k_smem + s * kv_bytes);
 #pragma unroll
         for (int k = 0; k < kDH5 / 16; ++k)
           umma_ss(tmem_base + b * kSCols5, qd + 2 * k, kd + 2 * k, idesc, k != 0 ? 1u : 0u);
         umma_commit(bar(C_SFULL + b));
-        umma_commit(bar(C_KEMPTY + b));
+        umma_commit(bar(C_KEMPTY + s));     // one of the nqt commits + 8 nqt norm-read arrivals that free the stage
         umma_commit(bar(C_QEMPTY + b));
       }
       __syncwarp();
@@ -315,17 +375,16 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     if (n_items > 0) issue_scores(0);
     if (n_items > 1) issue_scores(1);
 #ifdef VT_ATTN5_DBG
-    unsigned macc[4] = {0, 0, 0, 0};
-    unsigned mt = static_cast<unsigned>(clock());
-#define VT_MTICK(i) { const unsigned t_ = static_cast<unsigned>(clock()); macc[i] += t_ - mt; mt = t_; }
-#else
-#define VT_MTICK(i)
+    for (int i = 0; i < 6; ++i) macc[i] = 0;
+    mt = static_cast<unsigned>(clock());
 #endif
     for (int v = 0; v < n_items; ++v) {
       const int b = v & 1;
       const uint32_t ph = (static_cast<uint32_t>(v) >> 1) & 1u;
+      const int kvi = v >> kv_shift;
+      const int vs = kvi & 1;                  // V stage of the item's pair
       // ---- O_v = P_v V_v and the row sums P_v 1
-      mbar_wait(bar(C_VFULL + b), ph);
+      mbar_wait(bar(C_VFULL + vs), (static_cast<uint32_t>(kvi) >> 1) & 1u);
       VT_MTICK(0)
       if (v > 0) mbar_wait(bar(C_OREAD), static_cast<uint32_t>(v - 1) & 1u);   // O columns free
       VT_MTICK(1)
@@ -336,7 +395,7 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       // round trip is on each softmax group's critical path.)  The ones tile is 16 K rows x 128 B; every
       // element is 1, so its swizzle is moot, and the per-step descriptor re-bases LBO onto it.
       const uint32_t idesc = make_idesc_bf16(kQTile5, kDH5 + 16, 0, 1);
-      const uint32_t v_tile = v_smem + b * kv_bytes;
+      const uint32_t v_tile = v_smem + vs * kv_bytes;
       const uint32_t s_tmem = tmem_base + b * kSCols5;
       // 16 keys: 8 packed P columns, 2048 B of V.  P of group k lives at the start of its owner's
       // columns: half 0 owns groups [0, ng0)
@@ -363,7 +422,7 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         for (int k = na0; k < ng0; ++k) pv_step(k, 1u);
         for (int k = ng0 + na1; k < n16; ++k) pv_step(k, 1u);
         umma_commit(bar(C_OFULL + b));
-        umma_commit(bar(C_VEMPTY + b));
+        umma_commit(bar(C_VEMPTY + vs));
       }
       __syncwarp();
 #else
@@ -373,17 +432,17 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       if (elect_one_sync()) {
         for (int k = 0; k < n16; ++k) pv_step(k, k != 0 ? 1u : 0u);
         umma_commit(bar(C_OFULL + b));
-        umma_commit(bar(C_VEMPTY + b));
+        umma_commit(bar(C_VEMPTY + vs));
       }
       __syncwarp();
 #endif
       if (v + 2 < n_items) issue_scores(v + 2);
-      VT_MTICK(3)
+      VT_MTICK(5)
     }
 #ifdef VT_ATTN5_DBG
     if (p.dbg != nullptr && lane == 0) {
       long long* d = p.dbg + (2LL * gridDim.x + blockIdx.x) * 8;
-      for (int i = 0; i < 4; ++i) d[i] = macc[i];
+      for (int i = 0; i < 6; ++i) d[i] = macc[i];
     }
 #endif
 #undef VT_MTICK
@@ -476,9 +535,45 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
 #define VT_TICK5(i)
 #define VT_TICK5_START()
 #endif
+    // Logit bound (see kLogitBound5): thread tg of the group squares key row tg and (tg >= 128) query row tg - 128
+    const int tg = threadIdx.x & 255;
+    const int wg = warp_idx & 7;
+    const int grp_bar = 9 + g;               // named barrier of the group's 256 threads
+    const uint32_t q_row = q_smem + g * kQBytes5 + (tg & 127) * 128;
+    const float bound_c = p.scale_log2 * p.scale_log2 * kBoundMargin5;
     uint32_t ph = 0;
     for (int v = g; v < n_items; v += 2, ph ^= 1u) {
       VT_TICK5_START()
+      // ---- while Q K^T of this item runs: max |q|^2 and max |k|^2 over the item's rows, out of the operand tiles.
+      // The tiles are released to the producer by the MMA's commit AND these eight warps (barrier counts 9).
+      bool fast;
+      {
+        const int kvi = v >> kv_shift;
+        const int ks = kvi & 1;
+        mbar_wait_lean5(bar(C_KFULL + ks), (static_cast<uint32_t>(kvi) >> 1) & 1u);
+        mbar_wait_lean5(bar(C_QFULL + g), ph);
+        float k2 = 0.f, q2 = 0.f;
+        if (tg < p.bkv) k2 = row_sumsq_bf16x64(k_smem + ks * kv_bytes + tg * 128, tg & 7);
+        if (tg >= 128) q2 = row_sumsq_bf16x64(q_row, tg & 7);
+        // non-negative floats order like their bit patterns; a NaN (sign clear) sorts above every number
+        const uint32_t k2m = __reduce_max_sync(0xffffffffu, __float_as_uint(k2) & 0x7fffffffu);
+        const uint32_t q2m = __reduce_max_sync(0xffffffffu, __float_as_uint(q2) & 0x7fffffffu);
+        uint32_t* slot = nrm + ((g * 2 + ((v >> 1) & 1)) << 4);     // double-buffered per item of the group
+        if (lane == 0) {
+          slot[wg] = q2m;
+          slot[8 + wg] = k2m;
+          mbar_arrive(bar(C_KEMPTY + ks));
+          mbar_arrive(bar(C_QEMPTY + g));
+        }
+        named_bar_sync(grp_bar, 256);
+        const uint4 qa = *reinterpret_cast<const uint4*>(slot), qb = *reinterpret_cast<const uint4*>(slot + 4);
+        const uint4 ka = *reinterpret_cast<const uint4*>(slot + 8), kb = *reinterpret_cast<const uint4*>(slot + 12);
+        const uint32_t qmx = max(max(max(qa.x, qa.y), max(qa.z, qa.w)), max(max(qb.x, qb.y), max(qb.z, qb.w)));
+        const uint32_t kmx = max(max(max(ka.x, ka.y), max(ka.z, ka.w)), max(max(kb.x, kb.y), max(kb.z, kb.w)));
+        // (a NaN or an infinity fails the comparison: such items take the exact two-pass path)
+        fast = !p.no_bound && (__uint_as_float(qmx) * __uint_as_float(kmx) * bound_c <= kLogitBound5 * kLogitBound5);
+      }
+      VT_TICK5(5)
       mbar_wait_lean5(bar(C_SFULL + g), ph);
       VT_TICK5(0)
       tc_fence_after();
@@ -488,23 +583,26 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       // its P rows stay undefined (MMA rows are independent, the rows are never stored).
       const bool live = desc.z * kQTile5 + rq * 32 < p.N;
       if (live) {
-        // pass 1: row max over my columns, exchanged with the other half of the row
-        float mx = -INFINITY;
-        switch (ng) {   // warp-uniform
-          case 7: mx = max_groups5<7>(t_mine, nvr); break;
-          case 6: mx = max_groups5<6>(t_mine, nvr); break;
-          case 5: mx = max_groups5<5>(t_mine, nvr); break;
-          case 4: mx = max_groups5<4>(t_mine, nvr); break;
-          case 3: mx = max_groups5<3>(t_mine, nvr); break;
-          case 2: mx = max_groups5<2>(t_mine, nvr); break;
-          case 1: mx = max_groups5<1>(t_mine, nvr); break;
-          default: break;
+        float m = 0.f;
+        if (!fast) {   // group-uniform
+          // pass 1: row max over my columns, exchanged with the other half of the row
+          float mx = -INFINITY;
+          switch (ng) {   // warp-uniform
+            case 7: mx = max_groups5<7>(t_mine, nvr); break;
+            case 6: mx = max_groups5<6>(t_mine, nvr); break;
+            case 5: mx = max_groups5<5>(t_mine, nvr); break;
+            case 4: mx = max_groups5<4>(t_mine, nvr); break;
+            case 3: mx = max_groups5<3>(t_mine, nvr); break;
+            case 2: mx = max_groups5<2>(t_mine, nvr); break;
+            case 1: mx = max_groups5<1>(t_mine, nvr); break;
+            default: break;
+          }
+          *x_mine = mx;
+          VT_TICK5(1)
+          named_bar_sync(bar_id, 64);
+          m = fmaxf(mx, *x_other) * p.scale_log2;
+          VT_TICK5(2)
         }
-        *x_mine = mx;
-        VT_TICK5(1)
-        named_bar_sync(bar_id, 64);
-        const float m = fmaxf(mx, *x_other) * p.scale_log2;
-        VT_TICK5(2)
         // (experiment, off by default) the groups take turns on the MUFU pipe: item v's exp pass starts when
         // item v - 1's (the other group's) is over
         if (kExpTurns5 && v > 0) mbar_wait_lean5(bar(C_XTOK + g), static_cast<uint32_t>((v - 1) >> 1) & 1u);
@@ -992,10 +1090,12 @@ attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
 }
 
 long long* g_attn5_dbg = nullptr;
+int g_attn5_bound = -1;     // -1: VT_ATTN_NO_BOUND decides; 0 / 1: forced off / on (developer hook)
 
 }  // namespace
 
 void attn5_set_debug_buffer(void* ptr) { g_attn5_dbg = static_cast<long long*>(ptr); }
+void attn5_set_bound(int mode) { g_attn5_bound = mode; }
 
 int attn5_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, int B, int H, int N,
                       int dh, long long qkv_row_stride, long long qkv_batch_stride,
@@ -1019,9 +1119,11 @@ int attn5_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, in
   if (p.total_items >= (1LL << 31)) return VT_ERR_UNSUPPORTED;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.reverse = reverse;
+  static const int no_bound = [] { const char* e = getenv("VT_ATTN_NO_BOUND"); return (e && e[0] == '1') ? 1 : 0; }();
+  p.no_bound = g_attn5_bound >= 0 ? (g_attn5_bound == 0) : no_bound;
   p.dbg = g_attn5_dbg;
   const int smem = 1024 + 2 * kQBytes5 + 4 * p.bkv * kDH5 * 2 + 4 * kStageBytes5 + kOnesBytes5s + 8 * C_NBARS + 8 +
-                   16 * kRing5 + 2 * 2 * kQTile5 * 4;
+                   16 * kRing5 + 2 * 2 * kQTile5 * 4 + 2 * 2 * 16 * 4;
   if (smem > kSmemLimit5) return VT_ERR_UNSUPPORTED;
 
   const uint64_t cols = static_cast<uint64_t>(H) * dh;
@@ -1040,7 +1142,8 @@ int attn5_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, in
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long grid = p.total_items < sms ? p.total_items : sms;
+  const long long pairs = static_cast<long long>(B) * H;     // a CTA walks whole (image, head) pairs
+  const long long grid = pairs < sms ? pairs : sms;
   attn5_fwd_kernel<<<static_cast<unsigned>(grid), kThreads5s, smem, stream>>>(tq, tk, tv, to, p);
   return static_cast<int>(cudaGetLastError());
 }

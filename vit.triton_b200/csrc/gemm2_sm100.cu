@@ -310,9 +310,16 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         const uint32_t a_dst = tiles_addr + s * kStageBytes;
         const uint32_t b_dst = a_dst + kABytes;
         if (elect_one_sync()) {
+#ifdef VT_G2_HALFB   // energy experiment (wrong results): every second K block re-uses the stale B stage
+          const bool skip_b = (kb & 1) != 0;
+          if (is_leader) mbar_arrive_expect_tx(full_bar(s), 2 * kStageBytes - (skip_b ? 2 * kBBytes : 0));
+          tma_load_2d_2cta(&tma_a, full_bar(s), a_dst, kb * kBKE, a_row, kEvictNormal);
+          if (!skip_b) tma_load_2d_2cta(&tma_b, full_bar(s), b_dst, kb * kBKE, b_row, kEvictLast);
+#else
           if (is_leader) mbar_arrive_expect_tx(full_bar(s), 2 * kStageBytes);
           tma_load_2d_2cta(&tma_a, full_bar(s), a_dst, kb * kBKE, a_row, kEvictNormal);
           tma_load_2d_2cta(&tma_b, full_bar(s), b_dst, kb * kBKE, b_row, kEvictLast);
+#endif
         }
         __syncwarp();
         if (++s == kStages) { s = 0; phase ^= 1u; }
