@@ -41,9 +41,48 @@ with torch.no_grad():
         m(x)
     _lib.event_hook = None
     torch.cuda.synchronize()
+from vit.utils import capture_cuda_graph
+# the same counters inside a CUDA-graph replay: the debug buffers are allocated (and their pointers baked into the
+# launches) at capture time, the last replay leaves its timestamps in them
+eager_bufs = list(bufs)
+bufs.clear()
+with torch.no_grad():
+    _lib.event_hook = hook
+    g, _ = capture_cuda_graph(m, x)
+    _lib.event_hook = None
+    for _ in range(20):
+        g.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"graph replay: {e0.elapsed_time(e1) / 50:.3f} ms per forward")
 agg = collections.OrderedDict()
-for key, b in bufs:
+for key, b in eager_bufs:
     agg.setdefault(key, []).append(b.view(148, 8).double())
+# launch skew and gaps from the absolute in-kernel timestamps of the last graph replay (48 GEMM launches)
+last = bufs[-48:]
+torch.cuda.synchronize()
+spans, skews, gaps = [], [], []
+prev_end = None
+for key, b in last:
+    d = b.view(148, 8)
+    st, en = d[:, 6], d[:, 6] + d[:, 7]
+    spans.append((en.max() - st.min()).item() / 1e3)
+    skews.append(((st.max() - st.min()).item() / 1e3, (en.max() - en.min()).item() / 1e3))
+    if prev_end is not None:
+        gaps.append((key, (st.min() - prev_end).item() / 1e3))
+    prev_end = en.max()
+print(f"GEMM launches of one forward: sum of (last CTA end - first CTA start) {sum(spans)/1e3:.3f} ms; "
+      f"mean start skew {sum(a for a, _ in skews)/len(skews):.1f} us, mean end skew {sum(b for _, b in skews)/len(skews):.1f} us")
+print("time from the end of a GEMM to the start of the next GEMM (us; attention sits inside the QKV -> out-proj gap):")
+print("  " + ", ".join(f"N={k[1]},K={k[2]}:{g:.1f}" for k, g in gaps[:8]))
+tot_ns = 0.0
+for (M, N, K, gelu, res), ds in agg.items():
+    tot_ns += torch.stack(ds).mean(0)[:, 7].mean().item() * len(ds) / 3
+print(f"sum of the in-kernel wall times of the GEMM launches of one forward: {tot_ns / 1e6:.3f} ms")
 for (M, N, K, gelu, res), ds in agg.items():
     d = torch.stack(ds).mean(0)
     tiles = -(-M // 256) * -(-N // 256)
@@ -52,4 +91,4 @@ for (M, N, K, gelu, res), ds in agg.items():
     print(f"M={M} N={N} K={K} gelu={gelu} res={res} x{len(ds)}: tiles/cluster {per:.1f}; total cyc {d[:,5].mean():.0f} (max {d[:,5].max():.0f}); per tile: "
           f"epi wait-tfull {d[:,0].mean()/per:.0f}, epi busy {d[:,1].mean()/per:.0f}, store-drain {d[:,6].mean()/per:.0f}, "
           f"mma wait-full {lead[:,2].mean()/per:.0f}, mma wait-tempty {lead[:,3].mean()/per:.0f}, prod wait-empty {d[:,4].mean()/per:.0f}, "
-          f"period {d[:,5].mean()/per:.0f}")
+          f"period {d[:,5].mean()/per:.0f}; in-kernel wall {d[:,7].mean()/1e3:.1f} us = SM clock {d[:,5].mean()/d[:,7].mean():.3f} GHz")

@@ -33,11 +33,15 @@ out.append("## Full capture (`--set full --clock-control none`), one row per cap
 out.append("| kernel | " + " | ".join(f"{lab} ({units[i]})" if units[i] else lab for i, lab in idx) + " |")
 out.append("|---|" + "---|" * len(idx))
 traffic = {}
+prev = ""
 for row in r[2:]:
     if len(row) <= ni: continue
     name = row[ni].split("(")[0].replace("void ", "").replace("unnamed>::", "")[:40]
     out.append(f"| `{name}` | " + " | ".join(row[i] for i, _ in idx) + " |")
-    if "gemm2" in name:
+    after_gather, prev = "patch_gather" in prev, name
+    # the four GEMMs of ONE layer (QKV, out-proj, fc1, fc2): not the token-mode patch-embedding GEMM that follows
+    # the gather, not the next layer's launches
+    if "gemm2" in name and not after_gather and len(traffic.get("per_launch", [])) < 4:
         rd = float(row[hdr.index("dram__bytes_read.sum")]); wr = float(row[hdr.index("dram__bytes_write.sum")])
         mult = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}[units[hdr.index("dram__bytes_read.sum")]]
         traffic.setdefault("per_launch", []).append((rd + wr) * mult)

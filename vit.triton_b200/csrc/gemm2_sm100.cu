@@ -287,6 +287,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   const int num_kb = (p.K + kBKE - 1) / kBKE;
   long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long dbg_t0 = p.dbg ? clock64() : 0;
+  unsigned long long dbg_ns0 = 0;
+  if (p.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_ns0));
   const int first_tile = static_cast<int>(cluster_id_x());
   const int tile_step = static_cast<int>(num_clusters_x());
 
@@ -310,16 +312,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         const uint32_t a_dst = tiles_addr + s * kStageBytes;
         const uint32_t b_dst = a_dst + kABytes;
         if (elect_one_sync()) {
-#ifdef VT_G2_HALFB   // energy experiment (wrong results): every second K block re-uses the stale B stage
-          const bool skip_b = (kb & 1) != 0;
-          if (is_leader) mbar_arrive_expect_tx(full_bar(s), 2 * kStageBytes - (skip_b ? 2 * kBBytes : 0));
-          tma_load_2d_2cta(&tma_a, full_bar(s), a_dst, kb * kBKE, a_row, kEvictNormal);
-          if (!skip_b) tma_load_2d_2cta(&tma_b, full_bar(s), b_dst, kb * kBKE, b_row, kEvictLast);
-#else
           if (is_leader) mbar_arrive_expect_tx(full_bar(s), 2 * kStageBytes);
           tma_load_2d_2cta(&tma_a, full_bar(s), a_dst, kb * kBKE, a_row, kEvictNormal);
           tma_load_2d_2cta(&tma_b, full_bar(s), b_dst, kb * kBKE, b_row, kEvictLast);
-#endif
         }
         __syncwarp();
         if (++s == kStages) { s = 0; phase ^= 1u; }
@@ -702,7 +697,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 
   if (p.dbg && lane == 0 && (warp_idx == kWarpProducer || warp_idx == kWarpMma || warp_idx == 0)) {
     long long* d = p.dbg + static_cast<long long>(blockIdx.x) * 8;
-    if (warp_idx == 0) { d[0] = dbg_acc[0]; d[1] = dbg_acc[1]; d[6] = dbg_acc[6]; d[5] = clock64() - dbg_t0; }
+    if (warp_idx == 0) {
+      d[0] = dbg_acc[0]; d[1] = dbg_acc[1]; d[6] = dbg_acc[6]; d[5] = clock64() - dbg_t0;
+      unsigned long long ns1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+      d[7] = static_cast<long long>(ns1 - dbg_ns0);      // wall time of the same interval: d[5] / d[7] = the real SM clock
+      d[6] = static_cast<long long>(dbg_ns0);            // absolute start (replaces the store-drain counter): launch skew / gaps
+    }
     if (warp_idx == kWarpMma) { d[2] = dbg_acc[2]; d[3] = dbg_acc[3]; }
     if (warp_idx == kWarpProducer) { d[4] = dbg_acc[4]; }
   }
