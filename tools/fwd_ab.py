@@ -21,6 +21,22 @@ def run(n):
         m(xs[i % 4])
     e.record(); torch.cuda.synchronize()
     return s.elapsed_time(e) / n
+from vit.utils import capture_cuda_graph
 with torch.no_grad():
     run(10)
-    print(" ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("VT_")) or "defaults", f": {run(100):.3f} ms/forward", flush=True)
+    eager = run(100)
+    g, out = capture_cuda_graph(m, xs[0])
+    def replay(n):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(n):
+            g.replay()
+        e.record(); torch.cuda.synchronize()
+        return s.elapsed_time(e) / n
+    replay(10)
+    graph = replay(100)
+    ref = m(xs[0])
+    g.replay(); torch.cuda.synchronize()
+    same = torch.equal(ref, out)
+    print(" ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("VT_")) or "defaults",
+          f": eager {eager:.3f} ms/forward, graph replay {graph:.3f} ms/forward (replay == eager: {same})", flush=True)

@@ -279,8 +279,9 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();                 // (VT_PDL) the QKV GEMM's output is read from here on
+  pdl_launch_dependents();
 
-  // Work list of this CTA: items blockIdx.x, blockIdx.x + grid, ...
   // Work list of this CTA: (image, head) pairs blockIdx.x, blockIdx.x + grid, ...; a pair is nqt (1 or 2) items,
   // its query tiles, which follow each other in the item sequence and SHARE one K and one V tile: item `it`
   // uses Q buffer / score buffer / softmax group it & 1 and K/V stage (it >> kv_shift) & 1.  (Round 2 first loaded
@@ -795,6 +796,8 @@ attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();
+  pdl_launch_dependents();
 
   const long long first_item = blockIdx.x;
   const long long item_step = gridDim.x;
@@ -1144,8 +1147,8 @@ int attn5_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, in
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long pairs = static_cast<long long>(B) * H;     // a CTA walks whole (image, head) pairs
   const long long grid = pairs < sms ? pairs : sms;
-  attn5_fwd_kernel<<<static_cast<unsigned>(grid), kThreads5s, smem, stream>>>(tq, tk, tv, to, p);
-  return static_cast<int>(cudaGetLastError());
+  return static_cast<int>(launch_maybe_pdl(attn5_fwd_kernel, dim3(static_cast<unsigned>(grid)), dim3(kThreads5s), smem, stream,
+                                           tq, tk, tv, to, p));
 }
 
 // Head dim 64 with N > 208 (several KV blocks per item, online softmax) and head dim 80 with any N:
@@ -1188,8 +1191,8 @@ static int launch_attn5mb(const void* q, const void* k, const void* v, void* out
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long grid = p.total_items < sms ? p.total_items : sms;
-  kern<<<static_cast<unsigned>(grid), kThreads5, smem, stream>>>(tq, tk, tv, to, tqt, tkt, tvt, p);
-  return static_cast<int>(cudaGetLastError());
+  return static_cast<int>(launch_maybe_pdl(kern, dim3(static_cast<unsigned>(grid)), dim3(kThreads5), smem, stream, tq, tk, tv, to,
+                                           tqt, tkt, tvt, p));
 }
 
 int attn5mb_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, int B, int H, int N,

@@ -282,6 +282,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // everything above touched only this CTA's own state: from here on the predecessor's output is read
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_kb = (p.K + kBKE - 1) / kBKE;
@@ -737,8 +740,7 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   int clusters = num_sms2() / 2;
   if (tiles < clusters) clusters = tiles;
-  kern<<<2 * clusters, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, tr, p);
-  return static_cast<int>(cudaGetLastError());
+  return static_cast<int>(launch_maybe_pdl(kern, dim3(2 * clusters), dim3(kThreads), Cfg::kSmemBytes, stream, ta, tb, to, tr, p));
 }
 
 }  // namespace
