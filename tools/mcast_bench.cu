@@ -198,6 +198,90 @@ stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
   cl_sync();
 }
 
+// mode 8: the barrier protocol a 2-CTA GEMM with a shared operand would use inside a 4-CTA cluster.  CTA rank r = 2p + h
+// (pair p, half h).  Per 32 KB stage a CTA receives a private 16 KB box (unicast, cta_group::2, completion credited to
+// its pair LEADER's barrier) and two 8 KB halves of a shared 16 KB box, one issued by itself and one by rank r ^ 2,
+// both multicast to {h, h + 2} (cta_group::2 + multicast: each destination's bytes must land on the leader barrier of the
+// DESTINATION's pair).  A leader expects 64 KB per stage (its own and its peer's 32 KB); empties need both leaders.
+constexpr uint32_t kPeerMaskB = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_2cta_b(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :: "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerMaskB), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta_mc(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :: "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerMaskB), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__global__ void __launch_bounds__(128, 1)
+pair_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant__ CUtensorMap tmap64, int iters, int total_rows,
+            int asym, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + kStages * kStageBytes;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (kStages + s); };
+  const uint32_t rank = cl_rank(), csz = cl_size();
+  const uint32_t h = rank & 1, p = (rank >> 1) & 1;
+  const bool leader = h == 0;
+  const int n_lead = csz == 4 ? 2 : 1;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), n_lead); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  cl_sync();
+  const int warp = threadIdx.x >> 5;
+  const uint32_t n128 = static_cast<uint32_t>(total_rows / 128);
+  if (warp == 1 && leader) {   // consumer = the pair leader: frees the stage in every CTA that writes into this pair
+    for (int j = 0; j < iters; ++j) {
+      const int s = j % kStages;
+      spin_wait(full(s), (j / kStages) & 1);
+      if (elect_one_sync())
+        for (uint32_t c = 0; c < csz; ++c) remote_arrive(empty(s), c);
+      __syncwarp();
+    }
+  }
+  if (warp == 0) {
+    const long long t0 = clock64();
+    int s = 0; uint32_t ph = 0;
+    uint32_t b_priv = (blockIdx.x * 7u) % n128, b_sh = ((blockIdx.x >> 2) * 4u + h + 64u) % n128;
+    for (int i = 0; i < iters; ++i) {
+      spin_wait(empty(s), ph ^ 1u);
+      const uint32_t dst = base + s * kStageBytes;
+      if (elect_one_sync()) {
+        if (leader) mbar_arrive_expect_tx(full(s), 2 * kStageBytes);
+        tma_load_2d_2cta_b(&tmap128, full(s), dst, 0, static_cast<int>(b_priv * 128));
+        if (csz == 4 && asym) {
+          if (p == 1)
+            for (uint32_t q = 0; q < 2; ++q)
+              tma_load_2d_2cta_mc(&tmap64, full(s), dst + 16384 + q * 8192, 0, static_cast<int>(b_sh * 128 + q * 64),
+                                  static_cast<uint16_t>((1u << h) | (1u << (h + 2))));
+        } else if (csz == 4)
+          tma_load_2d_2cta_mc(&tmap64, full(s), dst + 16384 + p * 8192, 0, static_cast<int>(b_sh * 128 + p * 64),
+                              static_cast<uint16_t>((1u << h) | (1u << (h + 2))));
+        else
+          tma_load_2d_2cta_b(&tmap128, full(s), dst + 16384, 0, static_cast<int>(b_sh * 128));
+      }
+      __syncwarp();
+      b_priv += 148u * 7u; while (b_priv >= n128) b_priv -= n128;
+      b_sh += 37u * 4u + 1u; while (b_sh >= n128) b_sh -= n128;
+      if (++s == kStages) { s = 0; ph ^= 1u; }
+    }
+    for (int s2 = 0; s2 < kStages; ++s2) {
+      const int uses = (iters - s2 + kStages - 1) / kStages;
+      if (uses > 0) spin_wait(empty(s2), (uses - 1) & 1);
+    }
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) { out[blockIdx.x * 2] = t1 - t0; out[blockIdx.x * 2 + 1] = csz; }
+  }
+  __syncthreads();
+  cl_sync();
+}
+
 int main(int argc, char** argv) {
   const int iters = argc > 1 ? atoi(argv[1]) : 4000;
   const int kblocks = argc > 2 ? atoi(argv[2]) : 1;   // 64-column blocks per row (12 = a K = 768 operand)
@@ -260,6 +344,36 @@ int main(int argc, char** argv) {
       if (rep == 2)
         printf("mode %d: %d CTAs in 4-clusters | received B/clk/SM avg %.1f (fastest %.1f slowest %.1f) | chip %.2f TB/s received | %.3f ms\n",
                mode, n4, bytes / (csum / 148), bytes / cmin, bytes / cmax, bytes * 148 / (ms * 1e-3) / 1e12, ms);
+    }
+  }
+  {   // mode 8
+    CUtensorMap t128, t64;
+    if (make_tmap_bf16_2d(&t128, buf, 64, total_rows, 64, 64, 128, TMAP_SW_128) ||
+        make_tmap_bf16_2d(&t64, buf, 64, total_rows, 64, 64, 64, TMAP_SW_128)) { printf("tmap failed\n"); return 1; }
+    cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    for (int pref = 0; pref < 3; ++pref) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(148); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute attrs[2];
+      attrs[0].id = cudaLaunchAttributeClusterDimension;
+      attrs[0].val.clusterDim.x = 2; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+      attrs[1].id = cudaLaunchAttributePreferredClusterDimension;
+      attrs[1].val.preferredClusterDim.x = 4; attrs[1].val.preferredClusterDim.y = 1; attrs[1].val.preferredClusterDim.z = 1;
+      cfg.attrs = attrs; cfg.numAttrs = pref ? 2 : 1;
+      const int asym = pref == 2;
+      for (int rep = 0; rep < 2; ++rep) {
+        cudaError_t rc = cudaLaunchKernelEx(&cfg, pair_kernel, t128, t64, iters, total_rows, asym, out);
+        cudaError_t rc2 = cudaDeviceSynchronize();
+        if (rc != cudaSuccess || rc2 != cudaSuccess) { printf("mode 8: launch %s / sync %s\n", cudaGetErrorString(rc), cudaGetErrorString(rc2)); return 1; }
+      }
+      std::vector<long long> h(148 * 2);
+      cudaMemcpy(h.data(), out, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      double c4 = 0, c2 = 0; int n4 = 0, n2 = 0;
+      for (int b = 0; b < 148; ++b) { if (h[2 * b + 1] == 4) { c4 += h[2 * b]; ++n4; } else { c2 += h[2 * b]; ++n2; } }
+      const double bytes = static_cast<double>(iters) * kStageBytes;
+      printf("mode 8 (pair-leader barriers, %s): %d CTAs in 4-clusters %.1f B/clk/SM received, %d CTAs in 2-clusters %.1f B/clk/SM\n",
+             pref == 2 ? "preferred cluster 4, BOTH shared halves issued by pair 1 only" : pref ? "preferred cluster 4, shared half multicast" : "clusters of 2, unicast", n4, n4 ? bytes / (c4 / n4) : 0.0, n2,
+             n2 ? bytes / (c2 / n2) : 0.0);
     }
   }
   return 0;

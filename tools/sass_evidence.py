@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "vit.triton_b200", "vit", "kernels", "libvitb200.so")
-MNEMONICS = ["UTCHMMA", "UTCQMMA", "UTCHMMA.2CTA", "UTCQMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "MUFU.EX2",
+MNEMONICS = ["UTCHMMA", "UTCQMMA", "UTCHMMA.2CTA", "UTCQMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMALDG*MULTICAST", "UTMASTG", "UTCBAR", "MUFU.EX2",
              "FFMA2", "HMMA", "LDGSTS", "RED.E", "ATOMG", "ST.E.STRONG.SYS", "LDG.E.STRONG.SYS"]
 
 
@@ -44,6 +44,8 @@ def main():
             continue
         op = m.group(1)
         cur["_instructions"] += 1
+        if op.startswith("UTMALDG") and ".MULTICAST" in op:
+            cur["UTMALDG*MULTICAST"] += 1
         for mn in MNEMONICS:
             if op == mn or (op.startswith(mn + ".") and not (mn in ("UTCHMMA", "UTCQMMA") and ".2CTA" in op)):
                 cur[mn] += 1

@@ -20,9 +20,14 @@
 //   scores; O and the row sums (second N = 16 MMA against a tile of ones) are shared by both groups:
 //   PV_v is issued only after group (v-1) & 1 has read O_{v-1}, half a period earlier.
 //
+//   A CTA walks (image, head) PAIRS; the query tiles of a pair are consecutive items (nqt = 1 or 2, one per group)
+//   and share ONE K and ONE V stage (stage = pair & 1): half the operand traffic, and a stage is requested three
+//   item periods before the MMA issuer needs it.
+//
 //   warps 0-7 / 8-15  softmax group 0 / 1: warp = 8 * group + 4 * column_half + row_quarter.  Per item:
-//                     wait S | row max + exchange | exp -> P | arrive P-ready — and straight on to the
-//                     group's next item.  They never touch O.
+//                     logit bound (max |q|^2, max |k|^2 from the operand tiles, while Q K^T runs) | wait S |
+//                     [row max + exchange, only when the bound fails] | exp -> P | arrive P-ready — and straight on
+//                     to the group's next item.  They never touch O.
 //   warp 16           TMA producer (decodes the items into a shared-memory ring, allocates TMEM)
 //   warp 17           MMA issuer: per item v: wait P_v, V_v, O_{v-1} read | PV_v (+ row sums) |
 //                     S_{v+2} = Q K^T into S[v & 1]

@@ -112,16 +112,6 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
-__device__ __forceinline__ uint32_t cluster_id_x() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t num_clusters_x() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
-  return r;
-}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -151,6 +141,24 @@ __device__ __forceinline__ void tma_load_2d_2cta(const CUtensorMap* m, uint32_t 
       : "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerMask), "r"(c0), "r"(c1),
         "l"(hint)
       : "memory");
+}
+
+// The same, multicast: the box lands at the same offset in every CTA of `mask` and each destination's bytes are
+// credited to the leader barrier of the DESTINATION's pair (checked with tools/mcast_bench.cu, mode 8).
+__device__ __forceinline__ void tma_load_2d_2cta_mc(const CUtensorMap* m, uint32_t bar, uint32_t dst,
+                                                    int c0, int c1, uint16_t mask, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".multicast::cluster.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5, %6;"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerMask), "r"(c0), "r"(c1), "h"(mask),
+        "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
 }
 
 __device__ __forceinline__ void umma_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
@@ -193,8 +201,7 @@ __device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float
 }
 
 // Arrive (once all prior MMAs of this thread completed) on the barrier at this offset in BOTH CTAs.
-__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
-  const uint16_t mask = 3;
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t mask) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
       "[%0], %1;"
@@ -215,10 +222,11 @@ __device__ __forceinline__ float2 gelu_epi2(float2 x) { return gelu_erf_poly_x2(
 #endif
 
 template <int EPI, typename Cfg, int PREC = 0>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 1)     // cluster dimensions come with the launch: 2, preferred 4
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const __grid_constant__ CUtensorMap tma_out,
-                  const __grid_constant__ CUtensorMap tma_res, const Gemm2Params p) {
+                  const __grid_constant__ CUtensorMap tma_res, const __grid_constant__ CUtensorMap tma_a64,
+                  const __grid_constant__ CUtensorMap tma_b64, const Gemm2Params p) {
   constexpr int kStages = Cfg::kStages;
   constexpr int kStageBufs = Cfg::kStageBufs;
   constexpr int kEpiBytes = Cfg::kEpiBytes;
@@ -252,8 +260,20 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   constexpr int kWarpMma = kEpiWarps + 3;
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = cluster_ctarank();
-  const bool is_leader = (cta_rank == 0);
+  // An aligned GROUP of four CTAs = two CTA pairs works through a list of SUPERTILES: two 256 x 256 tiles that share
+  // one operand (the same column block on two adjacent row blocks: B is shared; or, for the last row block of an odd
+  // count, two adjacent column blocks: A is shared).  The device launches a group either as ONE cluster of four (the
+  // preferred size, 132 of a B200's 148 SMs) — then each pair loads its private operand as before and only HALF of the
+  // shared one, multicast to the CTA of the same rank in the other pair, a quarter less operand traffic out of L2 — or
+  // as two regular clusters of two, which load everything themselves: the same work list and the same results.
+  const uint32_t cta_rank = cluster_ctarank();        // 0..1 or 0..3
+  const bool quad = cluster_nctarank() == 4;
+  const uint32_t half = cta_rank & 1u;                // CTA within its pair: rows [128 half, +128) of the pair tile
+  const int pair = static_cast<int>((blockIdx.x >> 1) & 1u);   // pair within the group (= cta_rank >> 1 in a cluster of four)
+  const bool is_leader = (half == 0);
+  const uint16_t pair_mask = static_cast<uint16_t>(3u << (cta_rank & 2u));          // both CTAs of my pair
+  const uint16_t cluster_mask = quad ? static_cast<uint16_t>(0xF) : static_cast<uint16_t>(3);
+  const uint16_t share_mask = static_cast<uint16_t>((1u << half) | (1u << (half + 2)));   // my rank in both pairs
 
   if (warp_idx == kWarpProducer && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -264,7 +284,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   if (warp_idx == kWarpMma && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);      // leader's producer arrive.expect_tx (covers both CTAs' bytes)
-      mbar_init(empty_bar(s), 1);     // multicast tcgen05.commit
+      mbar_init(empty_bar(s), quad ? 2 : 1);     // multicast tcgen05.commit of every pair that reads what I load
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);                 // multicast tcgen05.commit
@@ -286,14 +306,34 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   pdl_wait();
   pdl_launch_dependents();
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // supertiles: [0, main_st) = (row-block pair mp, column block n), n fastest; then the last row block of an odd
+  // count, column blocks in pairs (the second tile of the last one may lie right of the matrix: a ghost that loads
+  // zeros and stores nothing)
+  const int main_st = (p.num_m_tiles >> 1) * p.num_n_tiles;
+  const int num_tiles = main_st + ((p.num_m_tiles & 1) ? ((p.num_n_tiles + 1) >> 1) : 0);   // supertiles
+  // (row block, column block, shared operand: 0 = B, 1 = A) of MY pair's tile of supertile t
+  auto decode_tile = [&](int t, int& m_blk, int& n_blk) -> int {
+    int m_lin, share;
+    if (t < main_st) {
+      const int mp = t / p.num_n_tiles;
+      n_blk = t - mp * p.num_n_tiles;
+      m_lin = 2 * mp + pair;
+      share = 0;
+    } else {
+      m_lin = p.num_m_tiles - 1;
+      n_blk = 2 * (t - main_st) + pair;
+      share = 1;
+    }
+    m_blk = p.reverse ? p.num_m_tiles - 1 - m_lin : m_lin;
+    return share;
+  };
   const int num_kb = (p.K + kBKE - 1) / kBKE;
   long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long dbg_t0 = p.dbg ? clock64() : 0;
   unsigned long long dbg_ns0 = 0;
   if (p.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_ns0));
-  const int first_tile = static_cast<int>(cluster_id_x());
-  const int tile_step = static_cast<int>(num_clusters_x());
+  const int first_tile = static_cast<int>(blockIdx.x >> 2);
+  const int tile_step = static_cast<int>(gridDim.x >> 2);
 
   if (warp_idx == kWarpProducer) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -302,11 +342,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     int s = 0;
     uint32_t phase = 0;
     for (int t = first_tile; t < num_tiles; t += tile_step) {
-      int m_blk = t / p.num_n_tiles;
-      const int n_blk = t - m_blk * p.num_n_tiles;
-      if (p.reverse) m_blk = p.num_m_tiles - 1 - m_blk;
-      const int a_row = m_blk * (2 * BM) + static_cast<int>(cta_rank) * BM;
-      const int b_row = n_blk * BN + static_cast<int>(cta_rank) * BNH;
+      int m_blk, n_blk;
+      const int share = decode_tile(t, m_blk, n_blk);
+      const int a_row = m_blk * (2 * BM) + static_cast<int>(half) * BM;
+      const int b_row = n_blk * BN + static_cast<int>(half) * BNH;
       for (int kb = 0; kb < num_kb; ++kb) {
         long long w0 = 0;
         if (p.dbg) w0 = clock64();
@@ -316,8 +355,19 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         const uint32_t b_dst = a_dst + kABytes;
         if (elect_one_sync()) {
           if (is_leader) mbar_arrive_expect_tx(full_bar(s), 2 * kStageBytes);
-          tma_load_2d_2cta(&tma_a, full_bar(s), a_dst, kb * kBKE, a_row, kEvictNormal);
-          tma_load_2d_2cta(&tma_b, full_bar(s), b_dst, kb * kBKE, b_row, kEvictLast);
+          if (!quad) {
+            tma_load_2d_2cta(&tma_a, full_bar(s), a_dst, kb * kBKE, a_row, kEvictNormal);
+            tma_load_2d_2cta(&tma_b, full_bar(s), b_dst, kb * kBKE, b_row, kEvictLast);
+          } else if (share == 0) {
+            // rows [64 pair, +64) of the shared 128-row B box, into my smem and that of my rank in the other pair
+            tma_load_2d_2cta(&tma_a, full_bar(s), a_dst, kb * kBKE, a_row, kEvictNormal);
+            tma_load_2d_2cta_mc(&tma_b64, full_bar(s), b_dst + pair * (kBBytes / 2), kb * kBKE, b_row + pair * (BNH / 2),
+                                share_mask, kEvictLast);
+          } else {
+            tma_load_2d_2cta_mc(&tma_a64, full_bar(s), a_dst + pair * (kABytes / 2), kb * kBKE, a_row + pair * (BM / 2),
+                                share_mask, kEvictNormal);
+            tma_load_2d_2cta(&tma_b, full_bar(s), b_dst, kb * kBKE, b_row, kEvictLast);
+          }
         }
         __syncwarp();
         if (++s == kStages) { s = 0; phase ^= 1u; }
@@ -357,12 +407,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
               if (kFp8In) umma_ss_2cta_f8(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
               else umma_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            umma_commit_2cta(empty_bar(s));
+            umma_commit_2cta(empty_bar(s), cluster_mask);
           }
           __syncwarp();
           if (++s == kStages) { s = 0; phase ^= 1u; }
         }
-        if (elect_one_sync()) umma_commit_2cta(tfull_bar(as));
+        if (elect_one_sync()) umma_commit_2cta(tfull_bar(as), pair_mask);
         __syncwarp();
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
@@ -400,10 +450,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 #pragma unroll
     for (int i = 0; i < kRsRegs; ++i) rsn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     auto tile_origin = [&](int t, int& row0, int& col0) {
-      int m_blk = t / p.num_n_tiles;
-      const int n_blk = t - m_blk * p.num_n_tiles;
-      if (p.reverse) m_blk = p.num_m_tiles - 1 - m_blk;
-      row0 = m_blk * (2 * BM) + static_cast<int>(cta_rank) * BM + q * 32;
+      int m_blk, n_blk;
+      decode_tile(t, m_blk, n_blk);
+      row0 = m_blk * (2 * BM) + static_cast<int>(half) * BM + q * 32;
       col0 = n_blk * BN + cgrp * kColsPerWarp;
     };
     auto prefetch_operands = [&](int t) {
@@ -733,14 +782,40 @@ int num_sms2() {
 
 template <int EPI, typename Cfg, int PREC = 0>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
-            const CUtensorMap& tr, const Gemm2Params& p, cudaStream_t stream) {
+            const CUtensorMap& tr, const CUtensorMap& ta64, const CUtensorMap& tb64, const Gemm2Params& p,
+            cudaStream_t stream) {
   auto kern = gemm2_bf16_kernel<EPI, Cfg, PREC>;
   static int granted[kMaxDevices] = {0};
   if (const int rc_attr = ensure_dynamic_smem(kern, Cfg::kSmemBytes, granted)) return rc_attr;
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  int clusters = num_sms2() / 2;
-  if (tiles < clusters) clusters = tiles;
-  return static_cast<int>(launch_maybe_pdl(kern, dim3(2 * clusters), dim3(kThreads), Cfg::kSmemBytes, stream, ta, tb, to, tr, p));
+  const int supertiles = (p.num_m_tiles >> 1) * p.num_n_tiles + ((p.num_m_tiles & 1) ? ((p.num_n_tiles + 1) >> 1) : 0);
+  int groups = num_sms2() / 4;
+  if (supertiles < groups) groups = supertiles;
+  // regular clusters of 2 (one tcgen05 CTA pair), preferred clusters of 4 (two pairs that share an operand by TMA
+  // multicast; VT_GEMM_QUAD=0: pairs only), programmatic dependent launch
+  static const bool quad = [] { const char* e = getenv("VT_GEMM_QUAD"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(4 * groups);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[3];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+  ++na;
+  if (quad) {
+    attr[na].id = cudaLaunchAttributePreferredClusterDimension;
+    attr[na].val.preferredClusterDim.x = 4; attr[na].val.preferredClusterDim.y = 1; attr[na].val.preferredClusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tr, ta64, tb64, p));
 }
 
 }  // namespace
@@ -769,10 +844,14 @@ int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long l
   if ((reinterpret_cast<uintptr_t>(rowstats) | reinterpret_cast<uintptr_t>(stats_out)) & 7)
     return VT_ERR_ALIGN;
 
-  CUtensorMap ta, tb, to, tr;
+  CUtensorMap ta, tb, to, tr, ta64, tb64;
   int rc = make_tmap_bf16_2d(&ta, A, K, M, lda, BK, BM, TMAP_SW_128);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tb, Bt, K, N, ldb, BK, BNH, TMAP_SW_128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&ta64, A, K, M, lda, BK, BM / 2, TMAP_SW_128);     // half boxes of the shared operand
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tb64, Bt, K, N, ldb, BK, BNH / 2, TMAP_SW_128);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&to, out, N, M, ldo, kChunkCols, 32, TMAP_SW_128);
   if (rc) return rc;
@@ -833,7 +912,7 @@ int gemm2_bf16_tcgen05(const void* A, long long lda, const void* Bt, long long l
     return (e && (e[0] == '5' || e[0] == '6')) ? (e[0] - '0') : 0;
   }();
   if (gelu && forced_gelu) deep = (forced_gelu == 6);
-#define VT_G2_LAUNCH(E) (deep ? launch2<E, G2Deep>(ta, tb, to, tr, p, stream) : launch2<E, G2Wide>(ta, tb, to, tr, p, stream))
+#define VT_G2_LAUNCH(E) (deep ? launch2<E, G2Deep>(ta, tb, to, tr, ta64, tb64, p, stream) : launch2<E, G2Wide>(ta, tb, to, tr, ta64, tb64, p, stream))
   if (rowstats && !colsum) return gelu ? VT_G2_LAUNCH(EPI_LNF | EPI_NOCS | EPI_GELU) : VT_G2_LAUNCH(EPI_LNF | EPI_NOCS);
   if (rowstats) return gelu ? VT_G2_LAUNCH(EPI_LNF | EPI_GELU) : VT_G2_LAUNCH(EPI_LNF);
   if (gelu) return VT_G2_LAUNCH(EPI_GELU);
@@ -860,10 +939,14 @@ int gemm2_patch_tokens(const void* A, long long lda, const void* W, long long ld
   const long long M = static_cast<long long>(B) * tok_pad;
   if (M >= (1LL << 31)) return VT_ERR_UNSUPPORTED;
 
-  CUtensorMap ta, tb, to, tr;
+  CUtensorMap ta, tb, to, tr, ta64, tb64;
   int rc = make_tmap_bf16_2d(&ta, A, K, M, lda, BK, BM, TMAP_SW_128);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tb, W, K, D, ldw, BK, BNH, TMAP_SW_128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&ta64, A, K, M, lda, BK, BM / 2, TMAP_SW_128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tb64, W, K, D, ldw, BK, BNH / 2, TMAP_SW_128);
   if (rc) return rc;
   rc = make_tmap_bf16_3d(&to, out, D, tokens, B, D, static_cast<uint64_t>(tokens) * D, kChunkCols, 32, TMAP_SW_128);
   if (rc) return rc;
@@ -890,8 +973,8 @@ int gemm2_patch_tokens(const void* A, long long lda, const void* W, long long ld
   if (ideal > 6144) ideal = 6144;
   p.pace = static_cast<int>(ideal * 210 / 1000);
   p.pace_q = static_cast<int>(ideal * 50 / 1000);
-  return stats_out ? launch2<EPI_RES | EPI_STATS, G2Wide>(ta, tb, to, tr, p, stream)
-                   : launch2<EPI_RES, G2Wide>(ta, tb, to, tr, p, stream);
+  return stats_out ? launch2<EPI_RES | EPI_STATS, G2Wide>(ta, tb, to, tr, ta64, tb64, p, stream)
+                   : launch2<EPI_RES, G2Wide>(ta, tb, to, tr, ta64, tb64, p, stream);
 }
 
 // FP8 form (behind vt_gemm_fp8 / VT_FP8=1, off the bf16 headline metric): A [M,K] and Bt [N,K] are e4m3 bytes
@@ -911,10 +994,14 @@ int gemm2_fp8_tcgen05(const void* A, long long lda, const void* Bt, long long ld
        reinterpret_cast<uintptr_t>(colscale)) & 15)
     return VT_ERR_ALIGN;
 
-  CUtensorMap ta, tb, to, tr;
+  CUtensorMap ta, tb, to, tr, ta64, tb64;
   int rc = make_tmap_u8_2d(&ta, A, K, M, lda, 2 * BK, BM, TMAP_SW_128);
   if (rc) return rc;
   rc = make_tmap_u8_2d(&tb, Bt, K, N, ldb, 2 * BK, BNH, TMAP_SW_128);
+  if (rc) return rc;
+  rc = make_tmap_u8_2d(&ta64, A, K, M, lda, 2 * BK, BM / 2, TMAP_SW_128);
+  if (rc) return rc;
+  rc = make_tmap_u8_2d(&tb64, Bt, K, N, ldb, 2 * BK, BNH / 2, TMAP_SW_128);
   if (rc) return rc;
   if (out_e4m3) rc = make_tmap_u8_2d(&to, out, N, M, ldo, 128, 32, TMAP_SW_128);
   else rc = make_tmap_bf16_2d(&to, out, N, M, ldo, kChunkCols, 32, TMAP_SW_128);
@@ -947,11 +1034,11 @@ int gemm2_fp8_tcgen05(const void* A, long long lda, const void* Bt, long long ld
   p.pace = static_cast<int>(ideal * 210 / 1000);
   p.pace_q = static_cast<int>(ideal * 50 / 1000);
   if (out_e4m3)
-    return gelu ? launch2<EPI_CSCALE | EPI_GELU, G2Deep, 2>(ta, tb, to, tr, p, stream)
-                : launch2<EPI_CSCALE, G2Deep, 2>(ta, tb, to, tr, p, stream);
-  if (residual) return launch2<EPI_CSCALE | EPI_RES, G2Deep, 1>(ta, tb, to, tr, p, stream);
-  if (gelu) return launch2<EPI_CSCALE | EPI_GELU, G2Deep, 1>(ta, tb, to, tr, p, stream);
-  return launch2<EPI_CSCALE, G2Deep, 1>(ta, tb, to, tr, p, stream);
+    return gelu ? launch2<EPI_CSCALE | EPI_GELU, G2Deep, 2>(ta, tb, to, tr, ta64, tb64, p, stream)
+                : launch2<EPI_CSCALE, G2Deep, 2>(ta, tb, to, tr, ta64, tb64, p, stream);
+  if (residual) return launch2<EPI_CSCALE | EPI_RES, G2Deep, 1>(ta, tb, to, tr, ta64, tb64, p, stream);
+  if (gelu) return launch2<EPI_CSCALE | EPI_GELU, G2Deep, 1>(ta, tb, to, tr, ta64, tb64, p, stream);
+  return launch2<EPI_CSCALE, G2Deep, 1>(ta, tb, to, tr, ta64, tb64, p, stream);
 }
 
 }  // namespace vt
