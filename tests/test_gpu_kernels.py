@@ -358,10 +358,12 @@ def test_flash_attention_two_group_kernel_single_block(B, H, N, gain):
     assert torch.equal(sub, got[:1])
 
 
-@pytest.mark.parametrize("B,H,N", [(3, 6, 197), (2, 4, 100), (40, 12, 197)])
-def test_flash_attention_bounded_logit_path_vs_exact_path(B, H, N):
+@pytest.mark.parametrize("B,H,N,dh", [(3, 6, 197, 64), (2, 4, 100, 64), (40, 12, 197, 64), (3, 6, 577, 64), (2, 5, 257, 80),
+                                       (1, 3, 1000, 64)])
+def test_flash_attention_bounded_logit_path_vs_exact_path(B, H, N, dh):
     """attn5 skips the row-max pass for (image, head) items whose logits are bounded by |q||k| (Cauchy-Schwarz,
-    csrc/attn5_sm100.cu kLogitBound5) and keeps the exact two-pass softmax for the others.  Heads with gains
+    csrc/attn5_sm100.cu kLogitBound5) and keeps the exact two-pass softmax for the others (the multi-block kernel
+    always takes the exact online step: its shapes are here so the switch stays harmless for them).  Heads with gains
     0.5 ... 8 put both kinds of item (and the threshold region, gain 2) into ONE launch, alternating inside a CTA;
     softmax is shift-invariant, so the two paths must agree to rounding — and with the fp32 reference."""
     import ctypes
@@ -370,10 +372,12 @@ def test_flash_attention_bounded_logit_path_vs_exact_path(B, H, N):
     lib.vt_debug_set_attn_bound.argtypes = [ctypes.c_int]
     lib.vt_debug_set_attn_bound.restype = None
     gains = torch.tensor([0.5, 8.0, 1.0, 2.0, 4.0, 1.5, 2.2, 0.1, 3.0, 1.0, 6.0, 2.0], device=dev())[:H]
-    qkv = torch.randn(B, N, 3, H, 64, device=dev())
+    qkv = torch.randn(B, N, 3, H, dh, device=dev())
     qkv[:, :, :2] *= gains.view(1, 1, 1, H, 1)
     qkv[B // 2, :, 0, 0] *= 30.0          # one image whose first head is far over the bound
-    qkv = qkv.view(B, N, 3 * H * 64).bfloat16()
+    if N > 208:                           # multi-block kernel: one KV block over the bound, the others under it
+        qkv[0, 300 % N:, 1, H - 1] *= 40.0
+    qkv = qkv.view(B, N, 3 * H * dh).bfloat16()
     want = _attn_ref(qkv, H)
     try:
         lib.vt_debug_set_attn_bound(1)

@@ -92,3 +92,19 @@ for (M, N, K, gelu, res), ds in agg.items():
           f"epi wait-tfull {d[:,0].mean()/per:.0f}, epi busy {d[:,1].mean()/per:.0f}, store-drain {d[:,6].mean()/per:.0f}, "
           f"mma wait-full {lead[:,2].mean()/per:.0f}, mma wait-tempty {lead[:,3].mean()/per:.0f}, prod wait-empty {d[:,4].mean()/per:.0f}, "
           f"period {d[:,5].mean()/per:.0f}; in-kernel wall {d[:,7].mean()/1e3:.1f} us = SM clock {d[:,5].mean()/d[:,7].mean():.3f} GHz")
+
+# is the finishing spread tied to particular CTAs (SMs) or random?  per-CTA duration relative to the launch mean,
+# over the launches of one shape in the last graph replay
+import collections as _c
+by_shape = _c.OrderedDict()
+for key, b in last:
+    by_shape.setdefault(key, []).append(b.view(148, 8)[:, 7].double())
+for key, ws in by_shape.items():
+    w = torch.stack(ws)                      # [launches, 148] wall ns
+    rel = w / w.mean(1, keepdim=True)
+    per_cta = rel.mean(0)
+    grp = per_cta.view(37, 4).mean(1)
+    print(f"N={key[1]} K={key[2]}: per-CTA mean relative duration min {per_cta.min():.3f} max {per_cta.max():.3f}; "
+          f"std of the per-CTA means {per_cta.std():.4f}, mean std within a CTA over launches {rel.std(0).mean():.4f}; "
+          f"slowest groups {[int(i) for i in grp.argsort(descending=True)[:5]]} ({grp.max():.3f}), "
+          f"fastest {[int(i) for i in grp.argsort()[:5]]} ({grp.min():.3f})")

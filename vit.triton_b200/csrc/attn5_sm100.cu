@@ -763,7 +763,8 @@ attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
   const uint32_t stage_smem = smem_base + stage_off;
   const int ones_off = stage_off + 16 * kStage;
   const uint32_t ones_smem = smem_base + ones_off;
-  const int bar_off = ones_off + kOnesBytes5;
+  constexpr int kOnesB = (DH == kDH5) ? kOnesBytes5s : kOnesBytes5;   // dh 64: the 16 x 128 B tile behind the N = 80 PV MMA
+  const int bar_off = ones_off + kOnesB;
   const uint32_t bar_base = smem_base + bar_off;
   const uint32_t tmem_slot = bar_base + 8u * C_NBARS;
   const int slot_off = bar_off + 8 * C_NBARS;
@@ -790,7 +791,10 @@ attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     }
   }
   if (warp_idx == 0) {
-    reinterpret_cast<uint4*>(smem_gen + ones_off)[lane] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+#pragma unroll
+    for (int i = 0; i < kOnesB / 16 / 32; ++i)
+      reinterpret_cast<uint4*>(smem_gen + ones_off)[lane + 32 * i] =
+          make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     fence_proxy_async_smem();
   }
   if (warp_idx == 16) {
@@ -924,9 +928,18 @@ attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         const uint32_t s_tmem = tmem_base + g * kSCols5;
         for (int k = 0; k < n16; ++k) {   // 16 keys: 2048 B of the main V tile, 512 B of the tail tile
           const uint32_t a_tmem = s_tmem + (k < ng0 ? 8 * k : 16 * ng0 + 8 * (k - ng0));
-          umma_ts(tmem_base + kOCol5, a_tmem, vd + 128 * k, idesc, k != 0 ? 1u : 0u);
-          if (kDT) umma_ts(tmem_base + kOCol5 + kDH5, a_tmem, vtd + 32 * k, idesc_l, k != 0 ? 1u : 0u);
-          umma_ts(tmem_base + kLCol, a_tmem, od, idesc_l, k != 0 ? 1u : 0u);
+          if (kDT == 0) {
+            // head dim 64: ONE N = 80 MMA per 16 keys — V plus, one re-based leading-byte-offset away, a tile of
+            // ones whose first 16 columns give the row sums right behind O (as in attn5_fwd_kernel: the tensor pipe
+            // spends ~50 cycles on an MMA this small whatever its N); 244 -> 237 us per launch at 577 tokens
+            const uint32_t v_k = v_smem + g * kv_bytes + 2048u * k;
+            umma_ts(tmem_base + kOCol5, a_tmem, make_desc_mnmajor_sw128(v_k, ones_smem - v_k),
+                    make_idesc_bf16(kQTile5, kDH5 + 16, 0, 1), k != 0 ? 1u : 0u);
+          } else {
+            umma_ts(tmem_base + kOCol5, a_tmem, vd + 128 * k, idesc, k != 0 ? 1u : 0u);
+            umma_ts(tmem_base + kOCol5 + kDH5, a_tmem, vtd + 32 * k, idesc_l, k != 0 ? 1u : 0u);
+            umma_ts(tmem_base + kLCol, a_tmem, od, idesc_l, k != 0 ? 1u : 0u);
+          }
         }
         umma_commit(bar(C_OFULL + g));
         umma_commit(bar(C_VEMPTY + g));
@@ -1164,7 +1177,8 @@ static int launch_attn5mb(const void* q, const void* k, const void* v, void* out
                           long long out_batch_stride, const Attn5MbParams& p, cudaStream_t stream) {
   constexpr int kDT = DH - kDH5;
   constexpr int kStage = 32 * (DH / 2) * 2;
-  const int smem = 1024 + 2 * kQTile5 * DH * 2 + 4 * p.bkv * DH * 2 + 16 * kStage + kOnesBytes5 + 8 * C_NBARS + 8 +
+  const int smem = 1024 + 2 * kQTile5 * DH * 2 + 4 * p.bkv * DH * 2 + 16 * kStage + (DH == kDH5 ? kOnesBytes5s : kOnesBytes5) +
+                   8 * C_NBARS + 8 +
                    16 * kRing5 + 2 * 2 * kQTile5 * 4;
   if (smem > kSmemLimit5) return VT_ERR_UNSUPPORTED;
   const uint64_t cols = static_cast<uint64_t>(H) * DH;
