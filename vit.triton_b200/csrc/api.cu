@@ -22,6 +22,8 @@ int gemm2_bf16_tcgen05(const void*, long long, const void*, long long, void*, lo
 void gemm2_set_debug_buffer(void*);
 void attn5_set_debug_buffer(void*);
 void attn5_set_bound(int);
+void attn5_set_max_ctas(int);
+void gemm2_set_max_groups(int);
 int simt_gemm(const void*, const void*, void*, const void*, int, int, int, int, int,
               const long long*, const long long*, const long long*, float, int, int, cudaStream_t);
 int attn5_fwd_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long,
@@ -81,6 +83,12 @@ void vt_debug_set_attn_buffer(void* ptr) {
 // Developer hook: 0 = every attention item takes the exact two-pass softmax, 1 = items whose logits are bounded
 // skip the row-max pass (the default), -1 = back to the VT_ATTN_NO_BOUND environment default.
 void vt_debug_set_attn_bound(int mode) { vt::attn5_set_bound(mode); }
+// Developer hook (SM partitioning experiments): the 2-CTA GEMM launches at most `gemm_groups` groups of four CTAs and the
+// single-block attention kernel at most `attn_ctas` CTAs; 0 = all SMs.  Read at launch time (also during graph capture).
+void vt_debug_set_sm_partition(int gemm_groups, int attn_ctas) {
+  vt::gemm2_set_max_groups(gemm_groups);
+  vt::attn5_set_max_ctas(attn_ctas);
+}
 
 const char* vt_status_string(int status) {
   switch (status) {

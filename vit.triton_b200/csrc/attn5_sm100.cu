@@ -1111,12 +1111,14 @@ attn5mb_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
 }
 
 long long* g_attn5_dbg = nullptr;
+int g_attn5_max_ctas = 0;   // > 0: at most this many CTAs per attention launch (SM partitioning, see api.cu)
 int g_attn5_bound = -1;     // -1: VT_ATTN_NO_BOUND decides; 0 / 1: forced off / on (developer hook)
 
 }  // namespace
 
 void attn5_set_debug_buffer(void* ptr) { g_attn5_dbg = static_cast<long long*>(ptr); }
 void attn5_set_bound(int mode) { g_attn5_bound = mode; }
+void attn5_set_max_ctas(int n) { g_attn5_max_ctas = n; }
 
 int attn5_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, int B, int H, int N,
                       int dh, long long qkv_row_stride, long long qkv_batch_stride,
@@ -1164,6 +1166,7 @@ int attn5_fwd_tcgen05(const void* q, const void* k, const void* v, void* out, in
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long pairs = static_cast<long long>(B) * H;     // a CTA walks whole (image, head) pairs
+  if (g_attn5_max_ctas > 0 && g_attn5_max_ctas < sms) sms = g_attn5_max_ctas;
   const long long grid = pairs < sms ? pairs : sms;
   return static_cast<int>(launch_maybe_pdl(attn5_fwd_kernel, dim3(static_cast<unsigned>(grid)), dim3(kThreads5s), smem, stream,
                                            tq, tk, tv, to, p));

@@ -768,6 +768,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 }
 
 long long* g_dbg_buffer = nullptr;
+int g_max_groups2 = 0;      // > 0: at most this many groups of four CTAs per GEMM launch (SM partitioning, see api.cu)
 
 int g_num_sms2 = 0;
 int num_sms2() {
@@ -789,6 +790,7 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
   if (const int rc_attr = ensure_dynamic_smem(kern, Cfg::kSmemBytes, granted)) return rc_attr;
   const int supertiles = (p.num_m_tiles >> 1) * p.num_n_tiles + ((p.num_m_tiles & 1) ? ((p.num_n_tiles + 1) >> 1) : 0);
   int groups = num_sms2() / 4;
+  if (g_max_groups2 > 0 && g_max_groups2 < groups) groups = g_max_groups2;
   if (supertiles < groups) groups = supertiles;
   // regular clusters of 2 (one tcgen05 CTA pair), preferred clusters of 4 (two pairs that share an operand by TMA
   // multicast; VT_GEMM_QUAD=0: pairs only), programmatic dependent launch
@@ -821,6 +823,7 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
 }  // namespace
 
 void gemm2_set_debug_buffer(void* ptr) { g_dbg_buffer = static_cast<long long*>(ptr); }
+void gemm2_set_max_groups(int n) { g_max_groups2 = n; }
 
 // bf16 in / bf16 out 2-CTA GEMM.  Same argument meaning as gemm_bf16_tcgen05 (out dtype fixed), plus
 // the optional LayerNorm fold (rowstats [+ colsum]: the A operand is the un-normalised activation and
