@@ -137,8 +137,31 @@ __device__ __forceinline__ float max_groups5(uint32_t a, int nv) {
   return fmaxf(m0, m1);
 }
 
+// exp2 of two BOUNDED arguments (|x| <= 64: the bounded-logit path) on the FMA pipe instead of the MUFU:
+// x = n + f with n = rint(x) read out of the mantissa of x + 1.5 * 2^23, 2^f by a degree-3 polynomial on
+// [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16 rounding of P), 2^n added into the exponent field.
+// Six packed-fp32 instructions + two integer ones per pair against two MUFU slots (16 cycles of the
+// quarter-rate pipe): VT_ATTN5_POLY pairs of every eight take this route.
+__device__ __forceinline__ float2 ex2_poly_x2(float2 x) {
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);
+  const float2 xf = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(xf, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.0f, -1.0f), x);
+  float2 p = __ffma2_rn(f, make_float2(0.055170852690935135f, 0.055170852690935135f),
+                        make_float2(0.2426093965768814f, 0.2426093965768814f));
+  p = __ffma2_rn(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  p = __ffma2_rn(p, f, make_float2(0.9999281764030457f, 0.9999281764030457f));
+  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(xf.x) << 23)),
+                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(xf.y) << 23)));
+}
+// Measured at C2 / C4 (us per launch, two A/B rounds on one box): 0 pairs 70.9 / 49.1, 2 pairs 69.8 / 48.4,
+// 3 pairs 69.0 / 47.8, 4 pairs 70.7 / 48.7 (the FMA side becomes the longer one).
+#ifndef VT_ATTN5_POLY
+#define VT_ATTN5_POLY 3
+#endif
+
 // one group: p = exp2(s * scale - m) -> bf16x2 -> TMEM columns dst .. dst + 7
-template <bool MASKED>
+template <bool MASKED, bool BOUNDED = false>
 __device__ __forceinline__ void exp_group5(const uint32_t (&r)[16], uint32_t dst, int nv_in_group, float scale_log2,
                                            float m) {
   uint32_t pk[8];
@@ -147,8 +170,15 @@ __device__ __forceinline__ void exp_group5(const uint32_t (&r)[16], uint32_t dst
   for (int i = 0; i < 16; i += 2) {
     // one FFMA2 (sm_100 f32x2) for the two arguments
     const float2 a2 = __ffma2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sc2, nm2);
-    float p0 = ex2_approx(a2.x);
-    float p1 = ex2_approx(a2.y);
+    float p0, p1;
+    if (BOUNDED && VT_ATTN5_POLY > 0 && (8 - (i >> 1)) <= VT_ATTN5_POLY) {   // the last VT_ATTN5_POLY pairs of the group
+      const float2 pp = ex2_poly_x2(a2);
+      p0 = pp.x;
+      p1 = pp.y;
+    } else {
+      p0 = ex2_approx(a2.x);
+      p1 = ex2_approx(a2.y);
+    }
     if (MASKED) {
       if (i >= nv_in_group) p0 = 0.f;
       if (i + 1 >= nv_in_group) p1 = 0.f;
@@ -161,7 +191,7 @@ __device__ __forceinline__ void exp_group5(const uint32_t (&r)[16], uint32_t dst
 // p = exp2(s * scale - m) over the same NG groups; P (bf16x2) of group g overwrites TMEM columns
 // a + 8g .. a + 8g + 7 (scores this thread has already consumed).  Groups are loaded in pairs, the
 // next pair is in flight during the math of the current one.
-template <int NG>
+template <int NG, bool BOUNDED = false>
 __device__ __forceinline__ void exp_groups5(uint32_t a, int nv, float scale_log2, float m, uint32_t half_bar,
                                             int lane) {
   constexpr int kPairs = (NG + 1) / 2;
@@ -180,9 +210,9 @@ __device__ __forceinline__ void exp_groups5(uint32_t a, int nv, float scale_log2
       const int g = 2 * pr + h;
       if (g < NG) {
         if (g < NG - 1 || nv >= 16 * NG)
-          exp_group5<false>(r[pr][h], a + 8 * g, 16, scale_log2, m);
+          exp_group5<false, BOUNDED>(r[pr][h], a + 8 * g, 16, scale_log2, m);
         else
-          exp_group5<true>(r[pr][h], a + 8 * g, nv - 16 * (NG - 1), scale_log2, m);
+          exp_group5<true, BOUNDED>(r[pr][h], a + 8 * g, nv - 16 * (NG - 1), scale_log2, m);
       }
     }
 #ifdef VT_ATTN5_SPLIT
@@ -614,6 +644,18 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         if (kExpTurns5 && v > 0) mbar_wait_lean5(bar(C_XTOK + g), static_cast<uint32_t>((v - 1) >> 1) & 1u);
         VT_TICK5(4)
         // pass 2: exponentials; P overwrites my own consumed scores
+        if (VT_ATTN5_POLY > 0 && fast) {   // bounded arguments: part of the exponentials on the FMA pipe
+          switch (ng) {
+            case 7: exp_groups5<7, true>(t_mine, nvr, p.scale_log2, m, bar(C_PHALF + g), lane); break;
+            case 6: exp_groups5<6, true>(t_mine, nvr, p.scale_log2, m, bar(C_PHALF + g), lane); break;
+            case 5: exp_groups5<5, true>(t_mine, nvr, p.scale_log2, m, bar(C_PHALF + g), lane); break;
+            case 4: exp_groups5<4, true>(t_mine, nvr, p.scale_log2, m, bar(C_PHALF + g), lane); break;
+            case 3: exp_groups5<3, true>(t_mine, nvr, p.scale_log2, m, bar(C_PHALF + g), lane); break;
+            case 2: exp_groups5<2, true>(t_mine, nvr, p.scale_log2, m, bar(C_PHALF + g), lane); break;
+            case 1: exp_groups5<1, true>(t_mine, nvr, p.scale_log2, m, bar(C_PHALF + g), lane); break;
+            default: break;
+          }
+        } else
         switch (ng) {
           case 7: exp_groups5<7>(t_mine, nvr, p.scale_log2, m, bar(C_PHALF + g), lane); break;
           case 6: exp_groups5<6>(t_mine, nvr, p.scale_log2, m, bar(C_PHALF + g), lane); break;
