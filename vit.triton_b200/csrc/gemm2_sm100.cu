@@ -6,7 +6,9 @@
 // what the bf16 model runs.  Reference ops replaced: matmul_kernel (vit/kernels/matmul.py:40-108)
 // with its bias / GELU epilogue, and add_kernel (vit/vit.py:140,147) via the residual epilogue.
 //
-// A cluster of two CTAs (one TPC) owns a 256 x 256 output tile: CTA r holds rows [128r, 128r+128)
+// Launch: regular clusters of two, PREFERRED clusters of four (two pairs on two tiles that share an operand, which is
+// then loaded in halves and TMA-multicast to the other pair: see the kernel), programmatic stream serialisation.
+// A pair of CTAs (one TPC) owns a 256 x 256 output tile: CTA r holds rows [128r, 128r+128)
 // of the tile in its TMEM (128 lanes x 256 fp32 columns, double buffered = all 512 columns) and
 // loads A rows [128r, +128) and Bt rows [128r, +128) of every 64-wide K block, so each SM pulls
 // 32 KB per K block from L2 instead of 48 KB for the same number of MACs.  Only the leader CTA
