@@ -154,10 +154,13 @@ __device__ __forceinline__ float2 ex2_poly_x2(float2 x) {
   return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(xf.x) << 23)),
                      __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(xf.y) << 23)));
 }
-// Measured at C2 / C4 (us per launch, two A/B rounds on one box): 0 pairs 70.9 / 49.1, 2 pairs 69.8 / 48.4,
-// 3 pairs 69.0 / 47.8, 4 pairs 70.7 / 48.7 (the FMA side becomes the longer one).
+// Measured at C2 / C4 in isolation (us per launch, two A/B rounds on one box): 0 pairs 70.9 / 49.1, 2 pairs 69.8 / 48.4,
+// 3 pairs 69.0 / 47.8, 4 pairs 70.7 / 48.7 (the FMA side becomes the longer one) — and INSIDE the power-capped C2
+// forward, where the SM clock is 1.2 instead of 1.9 GHz and the kernel is bound by instruction issue rather than by HBM
+// latency (ms per forward over 100 graph replays, three rounds on one box): 1 pair 8.622, 2 pairs 8.588 - 8.628,
+// 3 pairs 8.664, 4 pairs 8.708, 5 pairs 8.775; 0 pairs 9.020 against 8.940 for 3 pairs on another box.  Two it is.
 #ifndef VT_ATTN5_POLY
-#define VT_ATTN5_POLY 3
+#define VT_ATTN5_POLY 2
 #endif
 
 // one group: p = exp2(s * scale - m) -> bf16x2 -> TMEM columns dst .. dst + 7
