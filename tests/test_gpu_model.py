@@ -135,6 +135,34 @@ def test_cuda_graph_replay_equals_eager():
     assert torch.equal(static_out, eager)
 
 
+def test_launch_modes_are_bit_identical(tmp_path):
+    """The GEMM launched as preferred clusters of four with the shared operand TMA-multicast + programmatic dependent
+    launch (the default) computes bit for bit what plain clusters of two launched one after the other compute
+    (VT_GEMM_QUAD=0 VT_PDL=0), eagerly and replayed from a CUDA graph; the bounded-logit attention path differs from the
+    exact one by rounding only.  The switches are read once per process: three worker processes."""
+    import subprocess
+    import sys
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "launch_mode_worker.py")
+    results = {}
+    for tag, env in (("default", {}), ("plain", {"VT_GEMM_QUAD": "0", "VT_PDL": "0"}), ("exact", {"VT_ATTN_NO_BOUND": "1"})):
+        path = str(tmp_path / f"{tag}.pt")
+        e = dict(os.environ)
+        for k in ("VT_GEMM_QUAD", "VT_PDL", "VT_ATTN_NO_BOUND"):
+            e.pop(k, None)
+        e.update(env)
+        proc = subprocess.run([sys.executable, worker, path], env=e, capture_output=True, text=True, timeout=600)
+        assert proc.returncode == 0, proc.stderr[-2000:]
+        results[tag] = torch.load(path)
+    d, pl, ex = results["default"], results["plain"], results["exact"]
+    assert set(d) == set(pl) and len(d) >= 6
+    for k in d:
+        assert torch.isfinite(d[k].float()).all(), k
+        assert torch.equal(d[k], pl[k]), f"{k}: clusters of four / dependent launch differ from the plain launch"
+    assert torch.equal(d["eager"], d["graph"])
+    err = (d["eager"].float() - ex["eager"].float()).abs().max().item()
+    assert 0.0 <= err <= 5e-2, f"bounded-logit attention vs exact softmax: max-abs {err}"
+
+
 def test_repack_after_weight_update():
     model, _ = _build("tiny-b", torch.bfloat16)
     x = hf_oracle.make_input("tiny-b", 2).to(DEV, torch.bfloat16)
